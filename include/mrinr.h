@@ -1,0 +1,147 @@
+/*
+ * mrinr.h -- C ABI of libmrinr.so: the B200 (sm_100a) implementation of the mri-inr hot path
+ * (modulated-SIREN dense forward + the tiling either side of it).
+ *
+ * Conventions
+ *   - Every pointer argument named `d_*` (or documented "device") is a CUDA device pointer owned by
+ *     the caller; the library never allocates or frees caller-visible buffers.  The only library-owned
+ *     object is the opaque `MrinrPacked` handle (re-tiled weights + layer-0 table).
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the
+ *     device, so every entry point is CUDA-graph capturable except pack/free.
+ *   - Return value: 0 = success; <0 = argument / shape / unsupported-configuration error (MRINR_E_*);
+ *     >0 = a cudaError_t.  `mrinr_last_error()` returns a thread-local message for the last failure.
+ *   - Row-major, fp32 at the boundary.  Integer indices (patch order, reflect indices, black mask)
+ *     are bit-exact with the reference; floating-point tolerances are stated per function.
+ *
+ * Reference = MatteoWohlrapp/mri-inr (file:line cited per entry point; the reference is pure
+ * Python/PyTorch and has no FFI of its own -- these are the functions a binding of this path
+ * would replace; INTEGRATION.md shows the ctypes stub).
+ */
+#ifndef MRINR_H_
+#define MRINR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRINR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MRINR_API __attribute__((visibility("default")))
+#else
+#define MRINR_API
+#endif
+
+/* error codes (negative) */
+#define MRINR_E_ARG          (-1)  /* null pointer / non-positive size */
+#define MRINR_E_UNSUPPORTED  (-2)  /* configuration outside what the kernels implement */
+#define MRINR_E_ALIGN        (-3)  /* pointer not 16-byte aligned */
+#define MRINR_E_ARCH         (-4)  /* device is not sm_100 */
+
+/* activation of the hidden synthesis layers: src/networks/modulated_siren.py:31-80 */
+#define MRINR_ACT_SINE   0
+#define MRINR_ACT_MORLET 1
+
+/* operand precision of the hidden-layer contractions in mrinr_siren_forward */
+#define MRINR_PREC_FP16  0   /* tcgen05 kind::f16, fp16 operands (11-bit significand), fp32 accumulate  -- default */
+#define MRINR_PREC_BF16  1   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate                       */
+#define MRINR_PREC_FP32  2   /* CUDA-core FFMA, fp32 throughout (exact-mode reference kernel)            */
+
+/* A view of the reference module's parameters (state_dict tensors, fp32, contiguous, on the device).
+ * Layout = src/networks/modulated_siren.py: SirenNet (:160-213), Modulator (:304-323), grid (:427-433). */
+typedef struct MrinrWeightsView {
+  int32_t dim_in;            /* must be 2                                                      */
+  int32_t dim_hidden;        /* H; tensor-core path requires 256, fp32 path H % 32 == 0, <=256 */
+  int32_t dim_out;           /* must be 1 (modulated_siren.py:451-455 squeezes it)             */
+  int32_t num_layers;        /* L hidden layers, 2..16                                         */
+  int32_t latent_dim;        /* Z, multiple of 4, <= 512                                       */
+  int32_t siren_patch_size;  /* S; coordinates per patch C = S*S                               */
+  float   w0;                /* hidden layers 1..L-1 and the output layer                      */
+  float   w0_initial;        /* layer 0                                                        */
+  int32_t activation;        /* MRINR_ACT_*; the output layer is always sine (:211-213)        */
+  int32_t reserved;
+  const float* d_grid;             /* [C,2]   "grid" buffer (the coordinates actually used, :448)   */
+  const float* const* d_net_weight;/* host array of L device pointers: [H,2], then [H,H]            */
+  const float* const* d_net_bias;  /* host array of L device pointers [H], or NULL (use_bias=False) */
+  const float* d_last_weight;      /* [1,H]                                                         */
+  const float* d_last_bias;        /* [1] or NULL                                                   */
+  const float* const* d_mod_weight;/* host array of L device pointers: [H,Z], then [H,H+Z]          */
+  const float* const* d_mod_bias;  /* host array of L device pointers [H]                           */
+} MrinrWeightsView;
+
+typedef struct MrinrPacked MrinrPacked;   /* opaque */
+
+/* ---- library ------------------------------------------------------------------------------------ */
+MRINR_API int         mrinr_abi_version(void);
+MRINR_API const char* mrinr_last_error(void);
+/* Number of kernel launches this library has enqueued since load (all threads). */
+MRINR_API int64_t     mrinr_launch_count(void);
+
+/* ---- weights ------------------------------------------------------------------------------------ */
+/* Re-tiles the parameters for the kernels (tensor-core operand layout for W_1..W_{L-1}, transposed fp32
+ * copies, the patch-independent layer-0 activation table sin(w0_initial*(W_0 g_c + b_0)) [C,H]).
+ * Replaces what nn.Module construction + load_state_dict + .to(device) prepare in the reference
+ * (test_mod_siren.py:96-120).  Synchronises `stream` before returning. */
+MRINR_API int  mrinr_pack_weights(const MrinrWeightsView* view, int precision, void* stream, MrinrPacked** out);
+MRINR_API void mrinr_free_packed(MrinrPacked* p);
+/* Copies the layer-0 table [C,H] fp32 to d_out (test/introspection hook). */
+MRINR_API int  mrinr_packed_layer0_table(const MrinrPacked* p, float* d_out, void* stream);
+
+/* ---- coordinate grid: modulated_siren.py:427-433 -------------------------------------------------- */
+/* d_out [S*S,2]: out[c] = (lin[c / S], lin[c % S]), lin = torch.linspace(-1,1,S).  Bit-exact. */
+MRINR_API int mrinr_make_grid(int32_t S, float* d_out, void* stream);
+
+/* ---- modulator: modulated_siren.py:325-343 (Modulator.forward) ------------------------------------ */
+/* d_latent [B,Z] -> d_mods [L,B,H]: h_0 = relu(A_0 z + c_0), h_i = relu(A_i [h_{i-1}; z] + c_i).
+ * All layers in one launch.  fp32 FFMA; tolerance vs the reference 1e-5 relative. */
+MRINR_API int mrinr_modulator_forward(const MrinrPacked* p, const float* d_latent, int64_t B, float* d_mods,
+                            void* stream);
+
+/* ---- synthesis network: modulated_siren.py:215-233 (SirenNet.forward) over the grid of every patch -- */
+/* d_mods [L,B,H] (>= 0), d_black [B] (nullable; 1 = patch is black -> its output rows are zero and its
+ * coordinates are never evaluated: filter_and_remember_black_patches / reintegrate_black_patches,
+ * src/util/tiling.py:244-303), d_out [B, S*S].  When d_black is given, d_workspace must hold
+ * mrinr_siren_workspace_bytes(B) bytes (compacted index list); otherwise it may be NULL.
+ * Precision as chosen at pack time.  Tolerance: max-abs 1e-3 on the output (north_star); the
+ * fp32 mode agrees with the reference to ~1e-5. */
+MRINR_API int64_t mrinr_siren_workspace_bytes(int64_t B);
+MRINR_API int mrinr_siren_forward(const MrinrPacked* p, const float* d_mods, const uint8_t* d_black, int64_t B,
+                        float* d_out, void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- tiling: src/util/tiling.py ------------------------------------------------------------------- */
+/* image_to_patches (tiling.py:10-64) for N same-sized images + classify_patches (:184-198).
+ * d_img [N,H,W] -> d_patches [N*nV*nH, O, O], d_black [N*nV*nH] (nullable; 1 iff fp32 mean < 1e-10).
+ * nV = ceil(H/I), nH = ceil(W/I); reflect padding (O-I)/2 plus bottom/right padding to a multiple
+ * of I.  Indices bit-exact.  Requires O >= I, (O-I) even, O % 4 == 0, pad < H, W. */
+MRINR_API int mrinr_image_to_patches(const float* d_img, int64_t N, int32_t H, int32_t W, int32_t O, int32_t I,
+                           float* d_patches, uint8_t* d_black, void* stream);
+
+/* classify_patches (tiling.py:184-198) over n_patches already-extracted patches of `elems` floats each:
+ * d_black[i] = 1 iff the fp32 mean of patch i is < 1e-10. */
+MRINR_API int mrinr_classify_patches(const float* d_patches, int64_t n_patches, int32_t elems, uint8_t* d_black,
+                           void* stream);
+
+/* patches_to_image_weighted_average (tiling.py:91-140) / patches_to_image (:143-181) for N images.
+ * d_tiles [N*nV*nH, K, K]; d_weights [K,K] (generate_weight_matrix, :67-88) or NULL for unit
+ * weights; d_black nullable (black tiles contribute 0 with their weight, :287-301);
+ * d_img [N, nV*I, nH*I].  Accumulation order equals F.fold's on CPU, so the result is bit-exact
+ * against the fp32 CPU reference. */
+MRINR_API int mrinr_patches_to_image(const float* d_tiles, const float* d_weights, const uint8_t* d_black,
+                           int64_t N, int32_t nV, int32_t nH, int32_t K, int32_t I, float* d_img,
+                           void* stream);
+
+/* ---- magnitude / normalisation epilogue ------------------------------------------------------------ */
+/* fastmri.complex_abs as called at src/data/preprocessing.py:58: d_in [n,2] -> d_out [n],
+ * sqrt(re*re + im*im) with separately rounded products (bit-exact against torch fp32). */
+MRINR_API int mrinr_complex_abs(const float* d_in, int64_t n, float* d_out, void* stream);
+/* normalize_scan (src/util/visualization.py:113-126; per volume at preprocessing.py:127-137):
+ * d_in [G, n] -> d_out [G, n], per group (x - min) / (max - min).  d_scratch: 2*G floats. Bit-exact. */
+MRINR_API int mrinr_minmax_normalize(const float* d_in, int64_t G, int64_t n, float* d_out, float* d_scratch,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRINR_H_ */

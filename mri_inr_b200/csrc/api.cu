@@ -1,0 +1,217 @@
+// C-ABI entry points that are not pure kernel wrappers: error plumbing, weight packing, dispatch of
+// the synthesis forward by precision mode.
+#include "common.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace mrinr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace mrinr
+
+using namespace mrinr;
+
+extern "C" int mrinr_abi_version(void) { return MRINR_ABI_VERSION; }
+extern "C" const char* mrinr_last_error(void) { return g_err; }
+extern "C" int64_t mrinr_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" void mrinr_free_packed(MrinrPacked* p) {
+  if (!p) return;
+  cudaFree(p->d_table0);
+  cudaFree(p->d_net_wT);
+  cudaFree(p->d_net_w16);
+  cudaFree(p->d_net_bias);
+  cudaFree(p->d_last_w);
+  cudaFree(p->d_last_b);
+  cudaFree(p->d_mod_wT);
+  cudaFree(p->d_mod_bias);
+  cudaFree(p->d_errflag);
+  delete p;
+}
+
+extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void* stream, MrinrPacked** out) {
+  MRINR_REQUIRE(v && out, MRINR_E_ARG, "mrinr_pack_weights: null argument");
+  *out = nullptr;
+  MRINR_REQUIRE(v->dim_in == 2, MRINR_E_UNSUPPORTED, "mrinr_pack_weights: dim_in must be 2 (got %d)", v->dim_in);
+  MRINR_REQUIRE(v->dim_out == 1, MRINR_E_UNSUPPORTED,
+                "mrinr_pack_weights: dim_out must be 1 (got %d); the reference squeezes it (modulated_siren.py:451)",
+                v->dim_out);
+  MRINR_REQUIRE(v->num_layers >= 2 && v->num_layers <= 16, MRINR_E_UNSUPPORTED,
+                "mrinr_pack_weights: num_layers must be in [2,16] (got %d)", v->num_layers);
+  MRINR_REQUIRE(v->dim_hidden >= 32 && v->dim_hidden <= 512 && v->dim_hidden % 32 == 0, MRINR_E_UNSUPPORTED,
+                "mrinr_pack_weights: dim_hidden must be a multiple of 32 in [32,512] (got %d)", v->dim_hidden);
+  MRINR_REQUIRE(v->latent_dim >= 4 && v->latent_dim <= 1024 && v->latent_dim % 4 == 0, MRINR_E_UNSUPPORTED,
+                "mrinr_pack_weights: latent_dim must be a multiple of 4 in [4,1024] (got %d)", v->latent_dim);
+  MRINR_REQUIRE(v->siren_patch_size >= 1 && v->siren_patch_size <= 1024, MRINR_E_UNSUPPORTED,
+                "mrinr_pack_weights: siren_patch_size out of range (%d)", v->siren_patch_size);
+  MRINR_REQUIRE(v->activation == MRINR_ACT_SINE || v->activation == MRINR_ACT_MORLET, MRINR_E_ARG,
+                "mrinr_pack_weights: unknown activation %d", v->activation);
+  MRINR_REQUIRE(precision == MRINR_PREC_FP16 || precision == MRINR_PREC_BF16 || precision == MRINR_PREC_FP32,
+                MRINR_E_ARG, "mrinr_pack_weights: unknown precision %d", precision);
+  if (precision != MRINR_PREC_FP32) {
+    MRINR_REQUIRE(v->dim_hidden == 256, MRINR_E_UNSUPPORTED,
+                  "mrinr_pack_weights: the tensor-core path requires dim_hidden == 256 (got %d); use MRINR_PREC_FP32",
+                  v->dim_hidden);
+    MRINR_REQUIRE(v->siren_patch_size * v->siren_patch_size >= 128, MRINR_E_UNSUPPORTED,
+                  "mrinr_pack_weights: the tensor-core path requires siren_patch_size^2 >= 128 (got %d)",
+                  v->siren_patch_size);
+  }
+  MRINR_REQUIRE(v->d_grid && v->d_net_weight && v->d_last_weight && v->d_mod_weight && v->d_mod_bias, MRINR_E_ARG,
+                "mrinr_pack_weights: null weight pointer");
+  for (int l = 0; l < v->num_layers; ++l)
+    MRINR_REQUIRE(v->d_net_weight[l] && v->d_mod_weight[l] && v->d_mod_bias[l], MRINR_E_ARG,
+                  "mrinr_pack_weights: null pointer for layer %d", l);
+
+  int dev = 0;
+  MRINR_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MRINR_CUDA(cudaGetDeviceProperties(&prop, dev));
+  MRINR_REQUIRE(prop.major == 10, MRINR_E_ARCH, "mrinr_pack_weights: device %d is sm_%d%d; this library is sm_100a only",
+                dev, prop.major, prop.minor);
+
+  cudaStream_t st = (cudaStream_t)stream;
+  MrinrPacked* p = new (std::nothrow) MrinrPacked();
+  MRINR_REQUIRE(p, MRINR_E_ARG, "mrinr_pack_weights: out of host memory");
+  std::memset(p, 0, sizeof(*p));
+  p->H = v->dim_hidden; p->L = v->num_layers; p->Z = v->latent_dim; p->S = v->siren_patch_size;
+  p->C = p->S * p->S;
+  p->w0 = v->w0; p->w0_initial = v->w0_initial; p->activation = v->activation; p->precision = precision;
+  p->device = dev; p->num_sms = prop.multiProcessorCount;
+  const int H = p->H, L = p->L, Z = p->Z, C = p->C;
+
+  int rc = 0;
+#define PK_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      set_error("mrinr_pack_weights: %s failed: %s", #expr, cudaGetErrorString(_e));          \
+      rc = (int)_e;                                                                           \
+      goto fail;                                                                              \
+    }                                                                                         \
+  } while (0)
+#define PK_RC(expr)          \
+  do {                       \
+    rc = (expr);             \
+    if (rc != 0) goto fail;  \
+  } while (0)
+
+  {
+    const size_t mod_w_elems = (size_t)Z * H + (size_t)(L - 1) * (H + Z) * H;
+    PK_CUDA(cudaMalloc(&p->d_table0, (size_t)C * H * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_net_wT, (size_t)(L - 1) * H * H * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_net_w16, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
+    PK_CUDA(cudaMalloc(&p->d_net_bias, (size_t)L * H * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_last_w, (size_t)H * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_last_b, sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_mod_wT, mod_w_elems * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_mod_bias, (size_t)L * H * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_errflag, sizeof(int32_t)));
+    PK_CUDA(cudaMemsetAsync(p->d_errflag, 0, sizeof(int32_t), st));
+    PK_CUDA(cudaMemsetAsync(p->d_net_bias, 0, (size_t)L * H * sizeof(float), st));
+    PK_CUDA(cudaMemsetAsync(p->d_last_b, 0, sizeof(float), st));
+
+    const float* b0 = (v->d_net_bias && v->d_net_bias[0]) ? v->d_net_bias[0] : nullptr;
+    PK_RC(run_layer0_table(v->d_grid, v->d_net_weight[0], b0, C, H, p->w0_initial, p->activation, p->d_table0, st));
+    for (int l = 0; l < L; ++l) {
+      if (v->d_net_bias && v->d_net_bias[l])
+        PK_CUDA(cudaMemcpyAsync(p->d_net_bias + (size_t)l * H, v->d_net_bias[l], H * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+      PK_CUDA(cudaMemcpyAsync(p->d_mod_bias + (size_t)l * H, v->d_mod_bias[l], H * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+    }
+    for (int l = 1; l < L; ++l) {
+      PK_RC(run_transpose(v->d_net_weight[l], H, H, p->d_net_wT + (size_t)(l - 1) * H * H, st));
+      if (precision != MRINR_PREC_FP32)
+        PK_RC(run_pack_w16(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
+                           p->d_net_w16 + (size_t)(l - 1) * H * H, st));
+    }
+    PK_CUDA(cudaMemcpyAsync(p->d_last_w, v->d_last_weight, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (v->d_last_bias)
+      PK_CUDA(cudaMemcpyAsync(p->d_last_b, v->d_last_bias, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // modulator: layer 0 is [H,Z]; layers >= 1 are [H, H+Z] with the hidden columns first
+    float* dst = p->d_mod_wT;
+    PK_RC(run_transpose(v->d_mod_weight[0], H, Z, dst, st));
+    dst += (size_t)Z * H;
+    for (int l = 1; l < L; ++l) {
+      PK_RC(run_transpose(v->d_mod_weight[l], H, H + Z, dst, st));
+      dst += (size_t)(H + Z) * H;
+    }
+    PK_CUDA(cudaStreamSynchronize(st));
+  }
+  *out = p;
+  return 0;
+fail:
+  mrinr_free_packed(p);
+  return rc;
+#undef PK_CUDA
+#undef PK_RC
+}
+
+extern "C" int mrinr_packed_layer0_table(const MrinrPacked* p, float* d_out, void* stream) {
+  MRINR_REQUIRE(p && d_out, MRINR_E_ARG, "mrinr_packed_layer0_table: null argument");
+  MRINR_CUDA(cudaMemcpyAsync(d_out, p->d_table0, (size_t)p->C * p->H * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+  return 0;
+}
+
+// workspace layout: [0,16) n_active (int32) | idx int32[B] | blocksums int32[ceil(B/1024)]
+static inline size_t ws_idx_off() { return 16; }
+static inline size_t ws_bsum_off(int64_t B) { return 16 + (((size_t)B * 4 + 15) & ~(size_t)15); }
+
+extern "C" int64_t mrinr_siren_workspace_bytes(int64_t B) {
+  if (B < 0) return 0;
+  return (int64_t)(ws_bsum_off(B) + (((size_t)((B + 1023) / 1024) * 4 + 15) & ~(size_t)15) + 16);
+}
+
+extern "C" int mrinr_siren_forward(const MrinrPacked* p, const float* d_mods, const uint8_t* d_black, int64_t B,
+                                   float* d_out, void* d_workspace, int64_t workspace_bytes, void* stream) {
+  MRINR_REQUIRE(p && d_mods && d_out, MRINR_E_ARG, "mrinr_siren_forward: null pointer");
+  MRINR_REQUIRE(B >= 0 && B * (int64_t)p->C < ((int64_t)1 << 40), MRINR_E_ARG, "mrinr_siren_forward: bad batch %lld",
+                (long long)B);
+  MRINR_REQUIRE(B <= 0x7fffffff, MRINR_E_UNSUPPORTED, "mrinr_siren_forward: at most 2^31-1 patches per call");
+  MRINR_REQUIRE(aligned16(d_mods) && aligned16(d_out), MRINR_E_ALIGN, "mrinr_siren_forward: buffers must be 16-byte aligned");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t* d_idx = nullptr;
+  const int32_t* d_nactive = nullptr;
+  if (d_black != nullptr) {
+    MRINR_REQUIRE(d_workspace != nullptr && workspace_bytes >= mrinr_siren_workspace_bytes(B), MRINR_E_ARG,
+                  "mrinr_siren_forward: a black mask needs a workspace of mrinr_siren_workspace_bytes(B) bytes");
+    MRINR_REQUIRE(aligned16(d_workspace), MRINR_E_ALIGN, "mrinr_siren_forward: workspace must be 16-byte aligned");
+    char* ws = static_cast<char*>(d_workspace);
+    int32_t* nact = reinterpret_cast<int32_t*>(ws);
+    int32_t* idx = reinterpret_cast<int32_t*>(ws + ws_idx_off());
+    int32_t* bsum = reinterpret_cast<int32_t*>(ws + ws_bsum_off(B));
+    const int rc = launch_compact_black(d_black, B, p->C, idx, nact, bsum, d_out, st);
+    if (rc != 0) return rc;
+    d_idx = idx;
+    d_nactive = nact;
+  }
+  if (p->precision == MRINR_PREC_FP32) return launch_siren_fp32(p, d_mods, d_idx, d_nactive, B, d_out, st);
+  return launch_siren_tc(p, d_mods, d_idx, d_nactive, B, d_out, st);
+}

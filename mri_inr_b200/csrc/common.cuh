@@ -1,0 +1,71 @@
+// Shared host/device helpers for libmrinr (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mrinr.h"
+
+namespace mrinr {
+
+// ---- error plumbing (api.cu) -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int  check_launch(const char* what);   // cudaPeekAtLastError -> code (+message)
+
+#define MRINR_REQUIRE(cond, code, ...)            \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::mrinr::set_error(__VA_ARGS__);            \
+      return (code);                              \
+    }                                             \
+  } while (0)
+
+#define MRINR_CUDA(expr)                                                          \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ::mrinr::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));         \
+      return (int)_e;                                                             \
+    }                                                                             \
+  } while (0)
+
+__host__ __device__ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- packed weights (opaque to callers) ----------------------------------------------------------
+}  // namespace mrinr
+
+struct MrinrPacked {
+  int32_t H, L, Z, S, C;
+  float w0, w0_initial;
+  int32_t activation, precision;
+  int32_t device;
+  int32_t num_sms;
+  float*    d_table0;    // [C,H]  act_0(W_0 g_c + b_0), fp32 (before modulation)
+  float*    d_net_wT;    // [(L-1)][H(k)][H(n)]  fp32 transposed hidden weights (fp32 mode)
+  uint16_t* d_net_w16;   // [(L-1)][H/8 (kc)][H (n)][8]  fp16/bf16 UMMA K-major no-swizzle operand layout
+  float*    d_net_bias;  // [L][H]   (zeros when use_bias=False)
+  float*    d_last_w;    // [H]
+  float*    d_last_b;    // [1]
+  float*    d_mod_wT;    // layer 0: [Z][H]; layer i>=1: [(H+Z)][H] -- concatenated, transposed
+  float*    d_mod_bias;  // [L][H]
+  int32_t*  d_errflag;   // device-side watchdog flag (mbarrier timeouts)
+};
+
+namespace mrinr {
+
+int launch_siren_fp32(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx,
+                      const int32_t* d_nactive, int64_t B, float* d_out, cudaStream_t st);
+int launch_siren_tc(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx,
+                    const int32_t* d_nactive, int64_t B, float* d_out, cudaStream_t st);
+int run_transpose(const float* w, int N, int K, float* wT, cudaStream_t st);
+int run_pack_w16(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_t st);
+int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,
+                     int activation, float* table, cudaStream_t st);
+int launch_compact_black(const uint8_t* d_black, int64_t B, int32_t C, int32_t* d_idx, int32_t* d_nactive,
+                         int32_t* d_blocksums, float* d_out, cudaStream_t st);
+
+}  // namespace mrinr

@@ -1,0 +1,251 @@
+// fp32 CUDA-core kernels: weight re-tiling, the patch-independent layer-0 table, the modulator
+// (all layers, one launch) and the exact-mode (MRINR_PREC_FP32) synthesis kernel.
+//
+// Both dense kernels use the same scheme: a CTA owns TM=32 rows (patches for the modulator,
+// coordinates for the synthesis net), one thread per output column, activations ping-pong between
+// two shared-memory buffers across layers so nothing but the final result goes back to HBM; weights
+// are read through L1/L2 from a transposed [K][H] copy so that a warp's loads are one 128-byte line.
+#include "common.cuh"
+
+namespace mrinr {
+
+constexpr int TM = 32;
+
+// ---- pack-time kernels ----------------------------------------------------------------------------
+// wT[k][n] = W[n][k]
+__global__ void transpose_kernel(const float* __restrict__ w, int N, int K, float* __restrict__ wT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int k = i / N, n = i - k * N;
+  wT[i] = w[(long long)n * K + k];
+}
+
+// UMMA K-major / no-swizzle operand layout: out[kc][n][e] = cvt(W[n][8*kc + e]), kc = k/8.
+// A K=16 MMA step reads two consecutive kc slabs; slab stride (LBO) = H*16 bytes, 8-row group
+// stride (SBO) = 128 bytes.  See siren_tc.cu.
+__global__ void pack_w16_kernel(const float* __restrict__ w, int H, int use_bf16, uint16_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * H) return;
+  const int e = i & 7;
+  const int n = (i >> 3) % H;
+  const int kc = (i >> 3) / H;
+  const float v = w[(long long)n * H + kc * 8 + e];
+  uint16_t bits;
+  if (use_bf16) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&b);
+  } else {
+    const __half h = __float2half_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&h);
+  }
+  out[i] = bits;
+}
+
+__device__ __forceinline__ float act_exact(float pre, float w0, int activation) {
+  // Sine: modulated_siren.py:54 ; Morlet: :80 (Gaussian on the un-scaled pre-activation)
+  const float s = sinf(w0 * pre);
+  return activation == MRINR_ACT_MORLET ? s * expf(-0.5f * (pre * pre)) : s;
+}
+
+// table0[c][j] = act_0(W_0[j,:] . g_c + b_0[j])  -- every patch shares the coordinates
+// (modulated_siren.py:448), so layer 0 before modulation is patch independent.
+__global__ void layer0_table_kernel(const float* __restrict__ grid, const float* __restrict__ w0w,
+                                    const float* __restrict__ b0, int C, int H, float w0_initial,
+                                    int activation, float* __restrict__ table) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * H) return;
+  const int c = i / H, j = i - c * H;
+  const float gx = grid[2 * c], gy = grid[2 * c + 1];
+  float pre = __fmaf_rn(gy, w0w[2 * j + 1], __fmul_rn(gx, w0w[2 * j]));
+  if (b0) pre = __fadd_rn(pre, b0[j]);
+  table[i] = act_exact(pre, w0_initial, activation);
+}
+
+// ---- shared dense step ------------------------------------------------------------------------------
+// acc[r] += sum_k s_in[r*ld + k] * wT[k*H + j]   (k ascending, fp32 FFMA)
+__device__ __forceinline__ void dense_accumulate(const float* __restrict__ s_in, int ld, int K,
+                                                 const float* __restrict__ wT, int H, int j, float (&acc)[TM]) {
+  for (int k = 0; k < K; k += 4) {
+    const float w0 = __ldg(wT + (long long)(k + 0) * H + j);
+    const float w1 = __ldg(wT + (long long)(k + 1) * H + j);
+    const float w2 = __ldg(wT + (long long)(k + 2) * H + j);
+    const float w3 = __ldg(wT + (long long)(k + 3) * H + j);
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(s_in + r * ld + k);
+      acc[r] = fmaf(x.x, w0, acc[r]);
+      acc[r] = fmaf(x.y, w1, acc[r]);
+      acc[r] = fmaf(x.z, w2, acc[r]);
+      acc[r] = fmaf(x.w, w3, acc[r]);
+    }
+  }
+}
+
+// ---- modulator: modulated_siren.py:325-343 ------------------------------------------------------------
+// smem: z [TM][Z] | h [2][TM][H]
+__global__ void __launch_bounds__(512)
+modulator_kernel(const float* __restrict__ latent, long long B, int Z, int H, int L,
+                 const float* __restrict__ wT, const float* __restrict__ bias, float* __restrict__ mods) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_z = smem;
+  float* s_h = smem + TM * Z;
+  const int j = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * TM;
+  for (int i = threadIdx.x; i < TM * Z; i += blockDim.x) {
+    const int r = i / Z;
+    s_z[i] = (row0 + r < B) ? latent[(row0 + r) * Z + (i - r * Z)] : 0.f;
+  }
+  __syncthreads();
+  const float* w = wT;
+  for (int l = 0; l < L; ++l) {
+    float acc[TM];
+#pragma unroll
+    for (int r = 0; r < TM; ++r) acc[r] = 0.f;
+    float* h_out = s_h + (l & 1) * TM * H;
+    if (l > 0) {
+      // cat((x, z), dim=1): previous hidden first, then the latent (modulated_siren.py:341)
+      dense_accumulate(s_h + ((l - 1) & 1) * TM * H, H, H, w, H, j, acc);
+      w += (long long)H * H;
+    }
+    dense_accumulate(s_z, Z, Z, w, H, j, acc);
+    w += (long long)Z * H;
+    const float b = bias[l * H + j];
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      const float v = fmaxf(acc[r] + b, 0.f);
+      h_out[r * H + j] = v;
+      if (row0 + r < B) mods[((long long)l * B + row0 + r) * H + j] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- exact-mode synthesis kernel: SirenNet.forward, modulated_siren.py:215-233 -------------------------
+// smem: h [2][TM][H] | row bookkeeping
+__global__ void __launch_bounds__(512)
+siren_fp32_kernel(const float* __restrict__ table0, const float* __restrict__ wT, const float* __restrict__ bias,
+                  const float* __restrict__ last_w, const float* __restrict__ last_b,
+                  const float* __restrict__ mods, const int32_t* __restrict__ idx,
+                  const int32_t* __restrict__ nactive, long long B, int C, int H, int L, float w0,
+                  int activation, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_h = smem;
+  int* s_patch = reinterpret_cast<int*>(smem + 2 * TM * H);   // original patch index per row, -1 = padding
+  int* s_c = s_patch + TM;
+  const long long n_act = nactive ? (long long)*nactive : B;
+  const long long total_rows = n_act * C;
+  const long long n_tiles = (total_rows + TM - 1) / TM;
+  const int j = threadIdx.x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * TM;
+    __syncthreads();
+    if (threadIdx.x < TM) {
+      const long long R = row0 + threadIdx.x;
+      int patch = -1, c = 0;
+      if (R < total_rows) {
+        const long long pc = R / C;
+        c = (int)(R - pc * C);
+        patch = idx ? idx[pc] : (int)pc;
+      }
+      s_patch[threadIdx.x] = patch;
+      s_c[threadIdx.x] = c;
+    }
+    __syncthreads();
+    // layer 0 from the table, then modulation (modulated_siren.py:231)
+    for (int r = 0; r < TM; ++r) {
+      const int patch = s_patch[r];
+      float v = 0.f;
+      if (patch >= 0) v = table0[(long long)s_c[r] * H + j] * mods[((long long)0 * B + patch) * H + j];
+      s_h[r * H + j] = v;
+    }
+    __syncthreads();
+    for (int l = 1; l < L; ++l) {
+      float acc[TM];
+#pragma unroll
+      for (int r = 0; r < TM; ++r) acc[r] = 0.f;
+      const float* h_in = s_h + ((l - 1) & 1) * TM * H;
+      float* h_out = s_h + (l & 1) * TM * H;
+      dense_accumulate(h_in, H, H, wT + (long long)(l - 1) * H * H, H, j, acc);
+      const float b = bias[l * H + j];
+#pragma unroll
+      for (int r = 0; r < TM; ++r) {
+        const int patch = s_patch[r];
+        float v = 0.f;
+        if (patch >= 0) v = act_exact(acc[r] + b, w0, activation) * mods[((long long)l * B + patch) * H + j];
+        h_out[r * H + j] = v;
+      }
+      __syncthreads();
+    }
+    // output layer: always sine, not modulated (modulated_siren.py:211-213, :233)
+    const float* h_fin = s_h + ((L - 1) & 1) * TM * H;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = w; r < TM; r += nw) {
+      float s = 0.f;
+      for (int k = lane; k < H; k += 32) s = fmaf(h_fin[r * H + k], __ldg(last_w + k), s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const int patch = s_patch[r];
+      if (lane == 0 && patch >= 0) out[(long long)patch * C + s_c[r]] = sinf(w0 * (s + (last_b ? *last_b : 0.f)));
+    }
+  }
+}
+
+int run_transpose(const float* w, int N, int K, float* wT, cudaStream_t st) {
+  transpose_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(w, N, K, wT);
+  count_launch();
+  return check_launch("transpose");
+}
+
+int run_pack_w16(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_t st) {
+  pack_w16_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(w, H, use_bf16, out);
+  count_launch();
+  return check_launch("pack_w16");
+}
+
+int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,
+                     int activation, float* table, cudaStream_t st) {
+  layer0_table_kernel<<<(C * H + 255) / 256, 256, 0, st>>>(grid, w, b, C, H, w0_initial, activation, table);
+  count_launch();
+  return check_launch("layer0_table");
+}
+
+int launch_siren_fp32(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx,
+                      const int32_t* d_nactive, int64_t B, float* d_out, cudaStream_t st) {
+  const size_t smem = (size_t)2 * TM * p->H * sizeof(float) + 2 * TM * sizeof(int);
+  static int configured_for = -1;
+  if (configured_for != (int)smem) {
+    MRINR_CUDA(cudaFuncSetAttribute(siren_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_for = (int)smem;
+  }
+  const long long n_tiles = (B * p->C + TM - 1) / TM;
+  long long grid = (long long)p->num_sms * 2;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid < 1) grid = 1;
+  siren_fp32_kernel<<<(unsigned)grid, p->H, smem, st>>>(p->d_table0, p->d_net_wT, p->d_net_bias, p->d_last_w,
+                                                      p->d_last_b, d_mods, d_idx, d_nactive, B, p->C, p->H, p->L,
+                                                      p->w0, p->activation, d_out);
+  count_launch();
+  return check_launch("siren_fp32");
+}
+
+}  // namespace mrinr
+
+using namespace mrinr;
+
+extern "C" int mrinr_modulator_forward(const MrinrPacked* p, const float* d_latent, int64_t B, float* d_mods,
+                                       void* stream) {
+  MRINR_REQUIRE(p && d_latent && d_mods, MRINR_E_ARG, "mrinr_modulator_forward: null pointer");
+  MRINR_REQUIRE(B >= 0, MRINR_E_ARG, "mrinr_modulator_forward: negative batch");
+  if (B == 0) return 0;
+  const size_t smem = ((size_t)TM * p->Z + (size_t)2 * TM * p->H) * sizeof(float);
+  static int configured_for = -1;
+  if (configured_for != (int)smem) {
+    MRINR_CUDA(cudaFuncSetAttribute(modulator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_for = (int)smem;
+  }
+  const long long grid = (B + TM - 1) / TM;
+  modulator_kernel<<<(unsigned)grid, p->H, smem, (cudaStream_t)stream>>>(d_latent, B, p->Z, p->H, p->L, p->d_mod_wT,
+                                                                        p->d_mod_bias, d_mods);
+  count_launch();
+  return check_launch("modulator");
+}

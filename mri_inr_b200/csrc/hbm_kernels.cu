@@ -1,0 +1,422 @@
+// HBM-bound kernels of the mri-inr hot path: coordinate grid, overlapping-patch extraction with the
+// black-patch classifier, overlap (weighted) reassembly, complex magnitude, min-max normalisation,
+// and the black-patch compaction that feeds the synthesis kernels.
+//
+// All of these move each byte once: coalesced 16-byte accesses, grid sized to cover the data with
+// 256-thread CTAs (several waves over 148 SMs at production batch sizes).  Roofline: HBM bandwidth;
+// algorithmic bytes per slice are listed in DESIGN.md.
+#include "common.cuh"
+
+namespace mrinr {
+
+// ------------------------------------------------------------------------------------------------
+// grid: src/networks/modulated_siren.py:427-433.  torch.linspace(-1,1,S) on CPU evaluates
+// step=(end-start)/(S-1) in fp32 and lin[i] = i < S/2 ? start + step*i : end - step*(S-1-i),
+// each with a single rounding (vectorised fmadd).  __fmaf_rn reproduces it bit for bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float linspace_pm1(int i, int S, float step) {
+  if (S == 1) return -1.0f;
+  return (i < S / 2) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(S - 1 - i), 1.0f);
+}
+
+__global__ void make_grid_kernel(int S, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= S * S) return;
+  const float step = __fdiv_rn(2.0f, (float)(S - 1));
+  float2 g;
+  g.x = linspace_pm1(c / S, S, step);
+  g.y = linspace_pm1(c % S, S, step);
+  reinterpret_cast<float2*>(out)[c] = g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// image_to_patches (tiling.py:10-64) fused with classify_patches (tiling.py:184-198).
+// One warp per output patch; the O*O/4 float4 of a patch are written fully coalesced, the source
+// pixels are gathered through the reflect map (scalar read-only loads: each input pixel is read
+// (O/I)^2 = 4 times, from L1/L2 after the first).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int t, int n) {
+  t = t < 0 ? -t : t;
+  return t >= n ? 2 * (n - 1) - t : t;
+}
+
+__global__ void __launch_bounds__(256)
+image_to_patches_kernel(const float* __restrict__ img, long long n_patches, int H, int W, int O, int I,
+                        int nV, int nH, float* __restrict__ patches, uint8_t* __restrict__ black) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= n_patches) return;
+  const int per_img = nV * nH;
+  const long long n = warp / per_img;
+  const int p = (int)(warp - n * per_img);
+  const int py = p / nH, px = p - py * nH;
+  const int pad = (O - I) / 2;
+  const float* src = img + n * (long long)H * W;
+  float4* dst = reinterpret_cast<float4*>(patches + warp * (long long)O * O);
+  const int q_per_row = O / 4;
+  const int total_q = O * q_per_row;
+  const int y0 = I * py - pad, x0 = I * px - pad;
+  float sum = 0.f;
+  for (int q = lane; q < total_q; q += 32) {
+    const int r = q / q_per_row;
+    const int s = (q - r * q_per_row) * 4;
+    const float* row = src + (long long)reflect_idx(y0 + r, H) * W;
+    float4 v;
+    v.x = __ldg(row + reflect_idx(x0 + s + 0, W));
+    v.y = __ldg(row + reflect_idx(x0 + s + 1, W));
+    v.z = __ldg(row + reflect_idx(x0 + s + 2, W));
+    v.w = __ldg(row + reflect_idx(x0 + s + 3, W));
+    dst[q] = v;
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  if (black != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    // tile.mean() < 1e-10 (tiling.py:194-195); the summation order differs from torch's, which can
+    // only matter for a patch whose sum is within rounding of O*O*1e-10.
+    if (lane == 0) black[warp] = (sum / (float)(O * O) < 1e-10f) ? 1 : 0;
+  }
+}
+
+// classify_patches (tiling.py:184-198) on already extracted patches: one warp per patch.
+__global__ void __launch_bounds__(256)
+classify_patches_kernel(const float* __restrict__ patches, long long n_patches, int elems,
+                        uint8_t* __restrict__ black) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= n_patches) return;
+  const float* src = patches + warp * (long long)elems;
+  float sum = 0.f;
+  if ((elems & 3) == 0 && aligned16(src)) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int q = lane; q < elems / 4; q += 32) {
+      const float4 v = __ldg(s4 + q);
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int q = lane; q < elems; q += 32) sum += __ldg(src + q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) black[warp] = (sum / (float)elems < 1e-10f) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// patches_to_image_weighted_average (tiling.py:91-140) / patches_to_image (:143-181), gather form.
+// Output pixel (y,x) of image n receives tile[p][y+padq-I*py][x+padq-I*px] * w[..] from every patch
+// whose window covers it.  F.fold on CPU (col2im) adds contributions in increasing kernel-offset
+// order (ky,kx), i.e. decreasing py then decreasing px; the same order is used here so that the sums
+// -- and the final division -- are bit-identical to the fp32 CPU reference.
+// One thread per output pixel; consecutive threads read consecutive tile columns.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patches_to_image_kernel(const float* __restrict__ tiles, const float* __restrict__ weights,
+                        const uint8_t* __restrict__ black, long long n_pix, int nV, int nH, int K, int I,
+                        float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_pix) return;
+  const int OH = nV * I, OW = nH * I;
+  const long long n = gid / ((long long)OH * OW);
+  const int rem = (int)(gid - n * (long long)OH * OW);
+  const int y = rem / OW, x = rem - y * OW;
+  const int padq = (K - I) / 2;
+  const int yp = y + padq, xp = x + padq;
+  // patches py with 0 <= yp - I*py <= K-1
+  const int py_hi = min(yp / I, nV - 1);
+  const int py_lo = (yp - K + 1 <= 0) ? 0 : (yp - K + I) / I;   // ceil((yp-K+1)/I)
+  const int px_hi = min(xp / I, nH - 1);
+  const int px_lo = (xp - K + 1 <= 0) ? 0 : (xp - K + I) / I;
+  float acc = 0.f, norm = 0.f;
+  const long long pbase = n * (long long)nV * nH;
+  // increasing ky == decreasing py
+  for (int py = py_hi; py >= py_lo; --py) {
+    const int ky = yp - I * py;
+    for (int px = px_hi; px >= px_lo; --px) {
+      const int kx = xp - I * px;
+      const long long p = pbase + (long long)py * nH + px;
+      const float w = weights ? __ldg(weights + ky * K + kx) : 1.0f;
+      float t = 0.f;
+      if (black == nullptr || black[p] == 0) t = __ldg(tiles + p * (long long)K * K + ky * K + kx);
+      acc = __fadd_rn(acc, __fmul_rn(t, w));
+      norm = __fadd_rn(norm, w);
+    }
+  }
+  out[gid] = __fdiv_rn(acc, norm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// complex magnitude (fastmri.complex_abs at preprocessing.py:58): sqrt(re^2 + im^2), with the two
+// squares rounded separately as torch's (data**2).sum(-1).sqrt() does.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+complex_abs_kernel(const float2* __restrict__ in, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 v = __ldg(in + i);
+  out[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// min-max normalisation (visualization.py:113-126): two passes.  Pass 1 reduces min/max per group
+// with order-independent atomics on the float bit patterns; pass 2 applies (x-min)/(max-min).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int f2ord(float f) {   // monotone float -> uint map
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void minmax_init_kernel(unsigned int* scratch, long long G) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) { scratch[2 * g] = 0xffffffffu; scratch[2 * g + 1] = 0u; }
+}
+
+__global__ void __launch_bounds__(256)
+minmax_reduce_kernel(const float* __restrict__ in, long long n, unsigned int* __restrict__ scratch) {
+  const long long g = blockIdx.y;
+  const float* src = in + g * n;
+  float mn = INFINITY, mx = -INFINITY;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((n & 3) == 0 && aligned16(src)) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (; i < n / 4; i += stride) {
+      const float4 v = __ldg(s4 + i);
+      mn = fminf(fminf(mn, v.x), fminf(fminf(v.y, v.z), v.w));
+      mx = fmaxf(fmaxf(mx, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+    }
+  } else {
+    for (; i < n; i += stride) { const float v = __ldg(src + i); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ float smn[8], smx[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { smn[w] = mn; smx[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { mn = fminf(mn, smn[k]); mx = fmaxf(mx, smx[k]); }
+    atomicMin(scratch + 2 * g, f2ord(mn));
+    atomicMax(scratch + 2 * g + 1, f2ord(mx));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+minmax_apply_kernel(const float* __restrict__ in, long long n, const unsigned int* __restrict__ scratch,
+                    float* __restrict__ out) {
+  const long long g = blockIdx.y;
+  const float mn = ord2f(scratch[2 * g]);
+  const float range = __fsub_rn(ord2f(scratch[2 * g + 1]), mn);
+  const float* src = in + g * n;
+  float* dst = out + g * n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((n & 3) == 0 && aligned16(src) && aligned16(dst)) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (; i < n / 4; i += stride) {
+      float4 v = __ldg(s4 + i);
+      v.x = __fdiv_rn(__fsub_rn(v.x, mn), range);
+      v.y = __fdiv_rn(__fsub_rn(v.y, mn), range);
+      v.z = __fdiv_rn(__fsub_rn(v.z, mn), range);
+      v.w = __fdiv_rn(__fsub_rn(v.w, mn), range);
+      d4[i] = v;
+    }
+  } else {
+    for (; i < n; i += stride) dst[i] = __fdiv_rn(__fsub_rn(__ldg(src + i), mn), range);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Black-patch compaction (filter_and_remember_black_patches, tiling.py:244-271, as an index list):
+// idx[0..n_active) = ascending indices of the non-black patches; black patches' output rows are
+// zero-filled here (reintegrate_black_patches, tiling.py:274-303) so the synthesis kernel never
+// touches them.  Three small kernels: per-block counts, single-block exclusive scan, scatter.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCompactBlock = 1024;
+
+__global__ void __launch_bounds__(kCompactBlock)
+compact_count_kernel(const uint8_t* __restrict__ black, long long B, int32_t* __restrict__ blocksums) {
+  const long long i = (long long)blockIdx.x * kCompactBlock + threadIdx.x;
+  const int keep = (i < B && black[i] == 0) ? 1 : 0;
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) blocksums[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(int32_t* __restrict__ blocksums, int nblocks, int32_t* __restrict__ nactive) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? blocksums[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += u;
+      }
+      warp_tot[lane] = t;   // inclusive over warps
+    }
+    __syncthreads();
+    const int before = carry + (w > 0 ? warp_tot[w - 1] : 0) + incl - v;
+    if (i < nblocks) blocksums[i] = before;   // exclusive prefix
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *nactive = carry;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+compact_scatter_kernel(const uint8_t* __restrict__ black, long long B, const int32_t* __restrict__ blocksums,
+                       int32_t* __restrict__ idx) {
+  __shared__ int32_t warp_tot[32];
+  const long long i = (long long)blockIdx.x * kCompactBlock + threadIdx.x;
+  const int keep = (i < B && black[i] == 0) ? 1 : 0;
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_tot[w] = __popc(m);
+  __syncthreads();
+  if (w == 0) {
+    int t = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += u;
+    }
+    warp_tot[lane] = t;
+  }
+  __syncthreads();
+  if (keep) {
+    const int pos = blocksums[blockIdx.x] + (w > 0 ? warp_tot[w - 1] : 0) + __popc(m & ((1u << lane) - 1u));
+    idx[pos] = (int32_t)i;
+  }
+}
+
+// zero the output rows of black patches: one warp per patch
+__global__ void __launch_bounds__(256)
+zero_black_rows_kernel(const uint8_t* __restrict__ black, long long B, int C, float* __restrict__ out) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B || black[warp] == 0) return;
+  float* dst = out + warp * (long long)C;
+  for (int c = lane; c < C; c += 32) dst[c] = 0.f;
+}
+
+int launch_compact_black(const uint8_t* d_black, int64_t B, int32_t C, int32_t* d_idx, int32_t* d_nactive,
+                         int32_t* d_blocksums, float* d_out, cudaStream_t st) {
+  const int nblocks = (int)((B + kCompactBlock - 1) / kCompactBlock);
+  compact_count_kernel<<<nblocks, kCompactBlock, 0, st>>>(d_black, B, d_blocksums);
+  compact_scan_kernel<<<1, 1024, 0, st>>>(d_blocksums, nblocks, d_nactive);
+  compact_scatter_kernel<<<nblocks, kCompactBlock, 0, st>>>(d_black, B, d_blocksums, d_idx);
+  const long long threads = B * 32;
+  zero_black_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_black, B, C, d_out);
+  count_launch(4);
+  return check_launch("compact_black");
+}
+
+}  // namespace mrinr
+
+using namespace mrinr;
+
+extern "C" int mrinr_make_grid(int32_t S, float* d_out, void* stream) {
+  MRINR_REQUIRE(d_out != nullptr, MRINR_E_ARG, "mrinr_make_grid: null output");
+  MRINR_REQUIRE(S >= 1 && S <= 4096, MRINR_E_ARG, "mrinr_make_grid: S=%d out of range", S);
+  const int n = S * S;
+  make_grid_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, d_out);
+  count_launch();
+  return check_launch("make_grid");
+}
+
+extern "C" int mrinr_image_to_patches(const float* d_img, int64_t N, int32_t H, int32_t W, int32_t O, int32_t I,
+                                      float* d_patches, uint8_t* d_black, void* stream) {
+  MRINR_REQUIRE(d_img && d_patches, MRINR_E_ARG, "mrinr_image_to_patches: null pointer");
+  MRINR_REQUIRE(N >= 0 && H > 0 && W > 0 && O > 0 && I > 0, MRINR_E_ARG, "mrinr_image_to_patches: bad sizes");
+  MRINR_REQUIRE(O >= I && ((O - I) % 2) == 0 && (O % 4) == 0, MRINR_E_UNSUPPORTED,
+                "mrinr_image_to_patches: need O >= I, (O-I) even, O %% 4 == 0 (O=%d I=%d)", O, I);
+  const int pad = (O - I) / 2;
+  const int vpad = (I - H % I) % I, hpad = (I - W % I) % I;
+  // torch reflect padding requires pad < dim on every side (tiling.py:40-44)
+  MRINR_REQUIRE(pad + vpad < H && pad + hpad < W, MRINR_E_UNSUPPORTED,
+                "mrinr_image_to_patches: reflect padding %d/%d must be smaller than the image %dx%d",
+                pad + vpad, pad + hpad, H, W);
+  MRINR_REQUIRE(aligned16(d_patches), MRINR_E_ALIGN, "mrinr_image_to_patches: patches not 16-byte aligned");
+  if (N == 0) return 0;
+  const int nV = (H + vpad) / I, nH = (W + hpad) / I;
+  const long long n_patches = (long long)N * nV * nH;
+  const long long threads = n_patches * 32;
+  image_to_patches_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_img, n_patches, H, W, O, I, nV, nH, d_patches, d_black);
+  count_launch();
+  return check_launch("image_to_patches");
+}
+
+extern "C" int mrinr_classify_patches(const float* d_patches, int64_t n_patches, int32_t elems, uint8_t* d_black,
+                                      void* stream) {
+  MRINR_REQUIRE(d_patches && d_black && n_patches >= 0 && elems > 0, MRINR_E_ARG, "mrinr_classify_patches: bad arguments");
+  if (n_patches == 0) return 0;
+  const long long threads = (long long)n_patches * 32;
+  classify_patches_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_patches, n_patches,
+                                                                                             elems, d_black);
+  count_launch();
+  return check_launch("classify_patches");
+}
+
+extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weights, const uint8_t* d_black,
+                                      int64_t N, int32_t nV, int32_t nH, int32_t K, int32_t I, float* d_img,
+                                      void* stream) {
+  MRINR_REQUIRE(d_tiles && d_img, MRINR_E_ARG, "mrinr_patches_to_image: null pointer");
+  MRINR_REQUIRE(N >= 0 && nV > 0 && nH > 0 && K > 0 && I > 0 && K >= I && ((K - I) % 2) == 0, MRINR_E_ARG,
+                "mrinr_patches_to_image: bad sizes (K=%d I=%d)", K, I);
+  if (N == 0) return 0;
+  const long long n_pix = (long long)N * nV * I * nH * I;
+  patches_to_image_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_tiles, d_weights, d_black, n_pix, nV, nH, K, I, d_img);
+  count_launch();
+  return check_launch("patches_to_image");
+}
+
+extern "C" int mrinr_complex_abs(const float* d_in, int64_t n, float* d_out, void* stream) {
+  MRINR_REQUIRE(d_in && d_out && n >= 0, MRINR_E_ARG, "mrinr_complex_abs: bad arguments");
+  if (n == 0) return 0;
+  complex_abs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(d_in), n, d_out);
+  count_launch();
+  return check_launch("complex_abs");
+}
+
+extern "C" int mrinr_minmax_normalize(const float* d_in, int64_t G, int64_t n, float* d_out, float* d_scratch,
+                                      void* stream) {
+  MRINR_REQUIRE(d_in && d_out && d_scratch && G >= 0 && n > 0, MRINR_E_ARG, "mrinr_minmax_normalize: bad arguments");
+  MRINR_REQUIRE(G <= 65535, MRINR_E_UNSUPPORTED, "mrinr_minmax_normalize: at most 65535 groups per call");
+  if (G == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* scr = reinterpret_cast<unsigned int*>(d_scratch);
+  minmax_init_kernel<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(scr, G);
+  long long bx = (n / 4 + 255) / 256;
+  if (bx < 1) bx = 1;
+  if (bx > 592) bx = 592;   // 4 CTAs per SM x 148
+  dim3 grid((unsigned)bx, (unsigned)G);
+  minmax_reduce_kernel<<<grid, 256, 0, st>>>(d_in, n, scr);
+  minmax_apply_kernel<<<grid, 256, 0, st>>>(d_in, n, scr, d_out);
+  count_launch(3);
+  return check_launch("minmax_normalize");
+}

@@ -1,0 +1,242 @@
+"""Drop-in ``ModulatedSiren`` for the reference's ``src/networks/modulated_siren.py``.
+
+Same 17 constructor keyword arguments (modulated_siren.py:349-367, call site test_mod_siren.py:96-114),
+same ``state_dict`` layout (31 tensors: ``grid``, ``net.layers.{i}.{weight,bias}``, ``net.last_layer.*``,
+``modulator.layers.{i}.0.*``, ``encoder.encoder.encoder.{0,2,4,7}.*``) and the same
+``forward(tiles [B,32,32]) -> [B,S,S]`` (modulated_siren.py:435-457) -- but the forward is inference only
+and runs on the hand-written sm_100a kernels of ``libmrinr.so``:
+
+* modulator: one launch for all layers (``mrinr_modulator_forward``),
+* synthesis net over the coordinate grid of every patch: one persistent tcgen05 kernel
+  (``mrinr_siren_forward``); the coordinates are the module's ``grid`` buffer, as in the reference (:448).
+
+The patch encoder (3 convolutions + 1 linear, 0.3 % of the FLOPs) stays a PyTorch/cuDNN submodule
+(SURVEY.md section 8f #1).  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+import os
+import pathlib
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+
+__all__ = ["ModulatedSiren", "SirenNet", "Siren", "Modulator", "Encoder", "FixedEncoder", "make_grid_host"]
+
+
+def make_grid_host(siren_patch_size: int) -> torch.Tensor:
+    """The ``grid`` buffer ``[(h w), 2]`` exactly as ``torch.linspace``/``meshgrid(indexing="ij")`` build it
+    (modulated_siren.py:427-433), computed with the single-rounding symmetric formula."""
+    s = siren_patch_size
+    lin = np.empty(s, dtype=np.float32)
+    if s == 1:
+        lin[0] = -1.0
+    else:
+        step = np.float32(np.float32(2.0) / np.float32(s - 1))
+        for i in range(s):
+            if i < s // 2:
+                lin[i] = np.float32(np.float64(step) * i - 1.0)
+            else:
+                lin[i] = np.float32(1.0 - np.float64(step) * (s - 1 - i))
+    c = np.arange(s * s)
+    return torch.from_numpy(np.stack([lin[c // s], lin[c % s]], axis=1).astype(np.float32))
+
+
+class Siren(nn.Module):
+    """Parameter holder of one synthesis layer (``weight [out,in]``, ``bias [out]``); initialised with the
+    reference's ranges (``Siren.init_``, modulated_siren.py:126-142).  It has no forward of its own: the
+    whole network is evaluated by one fused kernel."""
+
+    def __init__(self, dim_in, dim_out, w0=1.0, c=6.0, is_first=False, use_bias=True, activation=None, dropout=0.0):
+        super().__init__()
+        self.dim_in, self.dim_out, self.w0, self.is_first = dim_in, dim_out, w0, is_first
+        self.activation_name = "morlet" if activation == "morlet" else "sine"
+        self.dropout_p = float(dropout)
+        bound = (1.0 / dim_in) if is_first else math.sqrt(c / dim_in) / w0
+        self.weight = nn.Parameter(torch.empty(dim_out, dim_in).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.empty(dim_out).uniform_(-bound, bound)) if use_bias else None
+
+    def forward(self, x):  # pragma: no cover - documented refusal
+        raise RuntimeError("mri_inr_b200.Siren holds parameters only; call ModulatedSiren / SirenNet instead")
+
+
+class SirenNet(nn.Module):
+    """``SirenNet`` (modulated_siren.py:160-233): ``num_layers`` hidden layers + a sine output layer."""
+
+    def __init__(self, dim_in, dim_hidden, dim_out, num_layers, w0, w0_initial, use_bias, dropout, activation):
+        super().__init__()
+        self.num_layers, self.dim_hidden = num_layers, dim_hidden
+        self.w0, self.w0_initial = float(w0), float(w0_initial)
+        self.layers = nn.ModuleList([
+            Siren(dim_in if i == 0 else dim_hidden, dim_hidden, w0=w0_initial if i == 0 else w0, is_first=(i == 0),
+                  use_bias=use_bias, activation=activation, dropout=dropout)
+            for i in range(num_layers)
+        ])
+        self.last_layer = Siren(dim_hidden, dim_out, w0=w0, use_bias=use_bias)
+
+    def forward(self, x, mods=None):  # pragma: no cover - documented refusal
+        raise RuntimeError("mri_inr_b200.SirenNet is evaluated through ModulatedSiren.forward / "
+                           "ModulatedSiren.synthesize(mods); per-call coordinates are not supported")
+
+
+class Modulator(nn.Module):
+    """``Modulator`` (modulated_siren.py:304-343).  ``forward`` runs the one-launch CUDA kernel."""
+
+    def __init__(self, dim_in, dim_hidden, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            nn.Sequential(nn.Linear(dim_in if i == 0 else dim_hidden + dim_in, dim_hidden), nn.ReLU())
+            for i in range(num_layers)
+        ])
+        self._owner = None  # set by ModulatedSiren (not a submodule reference: avoids a module cycle)
+
+    def forward(self, z):
+        if self._owner is None:
+            raise RuntimeError("Modulator must belong to a ModulatedSiren")
+        mods = ops.modulator_forward(self._owner()._packed(), z.contiguous())
+        return tuple(mods[i] for i in range(mods.shape[0]))
+
+
+def _encoder_stack(latent_dim: int) -> nn.Sequential:
+    # FixedAutoencoder.encoder (src/networks/encoding/siren_encoder.py:503-512): indices 0,2,4,7 carry parameters
+    return nn.Sequential(
+        nn.Conv2d(1, 16, 3, stride=2, padding=1), nn.LeakyReLU(0.2),
+        nn.Conv2d(16, 32, 3, stride=2, padding=1), nn.LeakyReLU(0.2),
+        nn.Conv2d(32, 64, 8), nn.LeakyReLU(0.2),
+        nn.Flatten(), nn.Linear(64, latent_dim),
+    )
+
+
+class FixedEncoder(nn.Module):
+    """``FixedEncoder`` (siren_encoder.py:551-577): the encoder half of the custom autoencoder, loaded from a
+    checkpoint with key ``"state_dict"`` (:544-549).  ``model_path=None`` leaves it randomly initialised."""
+
+    def __init__(self, model_path, device, latent_dim: int = 256):
+        super().__init__()
+        self.encoder = _encoder_stack(latent_dim)
+        if model_path is not None:
+            ckpt = torch.load(pathlib.Path(model_path), map_location=device)
+            sd = ckpt["state_dict"]
+            enc = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+            self.encoder.load_state_dict(enc, strict=True)
+        self.encoder.to(device)
+
+    def forward(self, x):
+        return self.encoder(x.unsqueeze(1))
+
+
+class Encoder(nn.Module):
+    """``Encoder`` (modulated_siren.py:236-301).  Only ``encoder_type="custom"`` is in scope."""
+
+    def __init__(self, latent_dim, encoder_path, device, encoder_type="custom"):
+        super().__init__()
+        self.latent_dim, self.encoder_type = latent_dim, encoder_type
+        if encoder_type != "custom":
+            raise NotImplementedError(
+                f"encoder_type={encoder_type!r}: only the 'custom' encoder is part of the B200 hot path "
+                "(the VGG ablation encoder is out of scope, SURVEY.md section 2)")
+        self.encoder = FixedEncoder(encoder_path, device, latent_dim)
+        self.fc = nn.Identity()
+
+    def forward(self, x):
+        # fp32 like the reference's eval path (no TF32: the CPU reference is plain fp32)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return self.fc(self.encoder(x))
+
+
+class ModulatedSiren(nn.Module):
+    """Drop-in for ``src.networks.modulated_siren.ModulatedSiren``.
+
+    Extra (non-reference) attribute: ``precision`` in {"fp16" (default), "bf16", "fp32"} -- operand format of
+    the hidden-layer tensor-core contractions; "fp32" selects the exact CUDA-core kernel.  The default can be
+    set with the environment variable ``MRINR_PRECISION``."""
+
+    def __init__(self, dim_in, dim_hidden, dim_out, num_layers, latent_dim, w0, w0_initial, use_bias, dropout,
+                 modulate, encoder_type, encoder_path, outer_patch_size, inner_patch_size, siren_patch_size, device,
+                 activation):
+        super().__init__()
+        self.dim_hidden, self.dim_out, self.num_layers, self.latent_dim = dim_hidden, dim_out, num_layers, latent_dim
+        self.modulate = modulate          # stored, never read: modulation is always applied (modulated_siren.py:397,446)
+        self.encoder_type = encoder_type
+        self.outer_patch_size, self.inner_patch_size = outer_patch_size, inner_patch_size
+        self.siren_patch_size = siren_patch_size
+        self.activation = activation
+        self.dropout = float(dropout)
+        self.precision = os.environ.get("MRINR_PRECISION", "fp16")
+
+        self.net = SirenNet(dim_in, dim_hidden, dim_out, num_layers, w0, w0_initial, use_bias, dropout, activation)
+        self.modulator = Modulator(latent_dim, dim_hidden, num_layers)
+        self.encoder = Encoder(latent_dim, encoder_path, device, encoder_type)
+        self.register_buffer("grid", make_grid_host(siren_patch_size))
+        import weakref
+
+        self.modulator._owner = weakref.ref(self)
+        self._pack_key = None
+        self._pack = None
+
+    # ---- packed weights: derived state, rebuilt when parameters change (load_state_dict, .to(), optimizer step)
+    def _pack_tensors(self) -> Sequence[Optional[torch.Tensor]]:
+        ts = [self.grid]
+        for layer in self.net.layers:
+            ts += [layer.weight, layer.bias]
+        ts += [self.net.last_layer.weight, self.net.last_layer.bias]
+        for seq in self.modulator.layers:
+            ts += [seq[0].weight, seq[0].bias]
+        return ts
+
+    def _packed(self) -> ops.PackedWeights:
+        ts = self._pack_tensors()
+        key = (self.precision, self.activation) + tuple(
+            (None if t is None else (t.data_ptr(), t._version, str(t.device))) for t in ts)
+        if self._pack is None or key != self._pack_key:
+            if not self.grid.is_cuda:
+                raise RuntimeError("mri_inr_b200.ModulatedSiren runs on CUDA only: call .to('cuda') first "
+                                   "(there is no CPU fallback)")
+            if self._pack is not None:
+                self._pack.free()
+            self._pack = ops.PackedWeights(
+                grid=self.grid,
+                net_weights=[l.weight for l in self.net.layers],
+                net_biases=[l.bias for l in self.net.layers],
+                last_weight=self.net.last_layer.weight, last_bias=self.net.last_layer.bias,
+                mod_weights=[s[0].weight for s in self.modulator.layers],
+                mod_biases=[s[0].bias for s in self.modulator.layers],
+                w0=self.net.w0, w0_initial=self.net.w0_initial, activation=self.activation,
+                precision=self.precision, siren_patch_size=self.siren_patch_size)
+            self._pack_key = key
+        return self._pack
+
+    def _check_inference(self) -> None:
+        if self.training and self.dropout > 0:
+            raise RuntimeError("mri_inr_b200.ModulatedSiren is inference only: call .eval() "
+                               "(the reference applies dropout in training mode, modulated_siren.py:124,156)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("mri_inr_b200.ModulatedSiren has no backward: call it under torch.no_grad() as "
+                               "test_mod_siren.py:131-132 does")
+
+    # ---- the two halves of forward, exposed for the batched pipeline
+    def modulations(self, tiles: torch.Tensor) -> torch.Tensor:
+        """``self.modulator(self.encoder(tiles))`` (modulated_siren.py:446) -> ``[L,B,H]``."""
+        z = self.encoder(tiles)
+        return ops.modulator_forward(self._packed(), z.contiguous())
+
+    def synthesize(self, mods: torch.Tensor, black: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``self.net(coords, mods)`` over the module's grid (modulated_siren.py:448-455) -> ``[B,S,S]``."""
+        s = self.siren_patch_size
+        y = ops.siren_forward(self._packed(), mods, black=black, out=out, workspace=workspace)
+        return y.view(-1, s, s)
+
+    def forward(self, tiles: torch.Tensor) -> torch.Tensor:
+        self._check_inference()
+        if not tiles.is_cuda:
+            raise RuntimeError("tiles must be a CUDA tensor: mri_inr_b200 has no CPU path")
+        if tiles.shape[0] == 0:
+            return tiles.new_zeros((0, self.siren_patch_size, self.siren_patch_size))
+        tiles = tiles.to(torch.float32).contiguous()
+        return self.synthesize(self.modulations(tiles))

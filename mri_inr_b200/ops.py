@@ -1,0 +1,254 @@
+"""Tensor-level wrappers of the C ABI (``include/mrinr.h``).  PyTorch is used only to own device memory
+and streams; every operation below is one or a few launches of the hand-written sm_100a kernels in
+``mri_inr_b200/csrc``.  All inputs must be CUDA tensors; nothing here falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def make_grid(siren_patch_size: int, device) -> torch.Tensor:
+    """Coordinate grid ``[S*S, 2]`` (src/networks/modulated_siren.py:427-433), generated on the device."""
+    lib = _lib.load()
+    device = torch.device(device)
+    out = torch.empty(siren_patch_size * siren_patch_size, 2, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.mrinr_make_grid(siren_patch_size, out.data_ptr(), _lib.stream_ptr(device)), "make_grid")
+    return out
+
+
+class PackedWeights:
+    """Owner of a ``MrinrPacked`` handle (re-tiled weights, layer-0 table)."""
+
+    def __init__(self, *, grid: torch.Tensor, net_weights: Sequence[torch.Tensor],
+                 net_biases: Sequence[Optional[torch.Tensor]], last_weight: torch.Tensor,
+                 last_bias: Optional[torch.Tensor], mod_weights: Sequence[torch.Tensor],
+                 mod_biases: Sequence[torch.Tensor], w0: float, w0_initial: float, activation: str,
+                 precision: str, siren_patch_size: int):
+        lib = _lib.load()
+        if activation not in _lib.ACTIVATIONS:
+            # the reference treats anything but "morlet" as sine (modulated_siren.py:120-123)
+            activation = "sine"
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        L = len(net_weights)
+        dev = grid.device
+        keep = []
+
+        def f32(t, name):
+            t = _lib.require_cuda(t.detach(), name)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(torch.float32).contiguous()
+            if t.device != dev:
+                raise RuntimeError(f"{name} is on {t.device}, expected {dev}")
+            keep.append(t)
+            return t
+
+        def ptr_array(ts, name):
+            arr = (c_void_p * L)()
+            for i, t in enumerate(ts):
+                arr[i] = None if t is None else f32(t, f"{name}[{i}]").data_ptr()
+            return arr
+
+        H = net_weights[0].shape[0]
+        view = _lib.WeightsView()
+        view.dim_in = net_weights[0].shape[1]
+        view.dim_hidden = H
+        view.dim_out = last_weight.shape[0]
+        view.num_layers = L
+        view.latent_dim = mod_weights[0].shape[1]
+        view.siren_patch_size = siren_patch_size
+        view.w0 = float(w0)
+        view.w0_initial = float(w0_initial)
+        view.activation = _lib.ACTIVATIONS[activation]
+        view.d_grid = f32(grid, "grid").data_ptr()
+        if tuple(grid.shape) != (siren_patch_size * siren_patch_size, 2):
+            raise RuntimeError(f"grid has shape {tuple(grid.shape)}, expected {(siren_patch_size ** 2, 2)}")
+        nw = ptr_array(net_weights, "net.layers.weight")
+        nb = ptr_array(net_biases, "net.layers.bias")
+        mw = ptr_array(mod_weights, "modulator.layers.weight")
+        mb = ptr_array(mod_biases, "modulator.layers.bias")
+        view.d_net_weight = ctypes.cast(nw, ctypes.POINTER(c_void_p))
+        view.d_net_bias = ctypes.cast(nb, ctypes.POINTER(c_void_p))
+        view.d_mod_weight = ctypes.cast(mw, ctypes.POINTER(c_void_p))
+        view.d_mod_bias = ctypes.cast(mb, ctypes.POINTER(c_void_p))
+        view.d_last_weight = f32(last_weight, "net.last_layer.weight").data_ptr()
+        view.d_last_bias = None if last_bias is None else f32(last_bias, "net.last_layer.bias").data_ptr()
+        handle = c_void_p()
+        with torch.cuda.device(dev):
+            rc = lib.mrinr_pack_weights(ctypes.byref(view), _lib.PRECISIONS[precision], _lib.stream_ptr(dev),
+                                        ctypes.byref(handle))
+        _lib.check(rc, "pack_weights")
+        self._handle = handle
+        self.device = dev
+        self.H, self.L, self.Z = H, L, view.latent_dim
+        self.S = siren_patch_size
+        self.C = siren_patch_size * siren_patch_size
+        self.precision = precision
+        self.activation = activation
+
+    @property
+    def handle(self) -> c_void_p:
+        if self._handle is None:
+            raise RuntimeError("PackedWeights already freed")
+        return self._handle
+
+    def free(self) -> None:
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().mrinr_free_packed(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def layer0_table(self) -> torch.Tensor:
+        out = torch.empty(self.C, self.H, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mrinr_packed_layer0_table(self.handle, out.data_ptr(), _lib.stream_ptr(self.device)),
+                       "packed_layer0_table")
+        return out
+
+
+def modulator_forward(packed: PackedWeights, latent: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``Modulator.forward`` (modulated_siren.py:325-343): latent ``[B,Z]`` -> mods ``[L,B,H]`` in one launch."""
+    lib = _lib.load()
+    _lib.require_cuda(latent, "latent", torch.float32)
+    if latent.dim() != 2 or latent.shape[1] != packed.Z:
+        raise RuntimeError(f"latent must be [B,{packed.Z}], got {tuple(latent.shape)}")
+    B = latent.shape[0]
+    if out is None:
+        out = torch.empty(packed.L, B, packed.H, dtype=torch.float32, device=latent.device)
+    else:
+        _lib.require_cuda(out, "out", torch.float32)
+        assert tuple(out.shape) == (packed.L, B, packed.H)
+    with torch.cuda.device(latent.device):
+        _lib.check(lib.mrinr_modulator_forward(packed.handle, latent.data_ptr(), B, out.data_ptr(),
+                                               _lib.stream_ptr(latent.device)), "modulator_forward")
+    return out
+
+
+def siren_forward(packed: PackedWeights, mods: torch.Tensor, black: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``SirenNet.forward`` over the grid of every patch (modulated_siren.py:215-233, :446-455):
+    mods ``[L,B,H]`` (+ optional black mask ``[B]`` uint8) -> ``[B, S*S]``."""
+    lib = _lib.load()
+    _lib.require_cuda(mods, "mods", torch.float32)
+    if mods.dim() != 3 or mods.shape[0] != packed.L or mods.shape[2] != packed.H:
+        raise RuntimeError(f"mods must be [{packed.L},B,{packed.H}], got {tuple(mods.shape)}")
+    B = mods.shape[1]
+    dev = mods.device
+    if out is None:
+        out = torch.empty(B, packed.C, dtype=torch.float32, device=dev)
+    else:
+        _lib.require_cuda(out, "out", torch.float32)
+        assert out.numel() == B * packed.C
+    ws_ptr, ws_bytes = None, 0
+    if black is not None:
+        _lib.require_cuda(black, "black", torch.uint8)
+        assert black.numel() == B
+        need = int(lib.mrinr_siren_workspace_bytes(B))
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws_ptr, ws_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mrinr_siren_forward(packed.handle, mods.data_ptr(), _ptr(black), B, out.data_ptr(), ws_ptr,
+                                           ws_bytes, _lib.stream_ptr(dev)), "siren_forward")
+    return out
+
+
+def image_to_patches(images: torch.Tensor, outer: int, inner: int, with_black_mask: bool = False,
+                     out: Optional[torch.Tensor] = None):
+    """``image_to_patches`` (src/util/tiling.py:10-64) for a batch ``[N,H,W]`` of equally sized images.
+    Returns ``(patches [N*nV*nH, outer, outer], (nV, nH), black_mask or None)``."""
+    lib = _lib.load()
+    _lib.require_cuda(images, "images", torch.float32)
+    if images.dim() != 3:
+        raise RuntimeError(f"images must be [N,H,W], got {tuple(images.shape)}")
+    N, H, W = images.shape
+    nV, nH = -(-H // inner), -(-W // inner)
+    dev = images.device
+    P = N * nV * nH
+    if out is None:
+        out = torch.empty(P, outer, outer, dtype=torch.float32, device=dev)
+    black = torch.empty(P, dtype=torch.uint8, device=dev) if with_black_mask else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.mrinr_image_to_patches(images.data_ptr(), N, H, W, outer, inner, out.data_ptr(), _ptr(black),
+                                              _lib.stream_ptr(dev)), "image_to_patches")
+    return out, (nV, nH), black
+
+
+def classify_patches(patches: torch.Tensor) -> torch.Tensor:
+    """``classify_patches`` (tiling.py:184-198) for every patch: uint8 mask, 1 = black (mean < 1e-10)."""
+    lib = _lib.load()
+    _lib.require_cuda(patches, "patches", torch.float32)
+    n = patches.shape[0]
+    elems = patches[0].numel() if n > 0 else 1
+    black = torch.empty(n, dtype=torch.uint8, device=patches.device)
+    with torch.cuda.device(patches.device):
+        _lib.check(lib.mrinr_classify_patches(patches.data_ptr(), n, elems, black.data_ptr(),
+                                              _lib.stream_ptr(patches.device)), "classify_patches")
+    return black
+
+
+def patches_to_image(tiles: torch.Tensor, n_images: int, grid_shape: Tuple[int, int], inner: int,
+                     weights: Optional[torch.Tensor] = None, black: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Overlap reassembly (tiling.py:91-181) of ``n_images`` images -> ``[N, nV*inner, nH*inner]``."""
+    lib = _lib.load()
+    _lib.require_cuda(tiles, "tiles", torch.float32)
+    nV, nH = grid_shape
+    K = tiles.shape[-1]
+    if tiles.shape[0] != n_images * nV * nH or tiles.shape[-2] != K:
+        raise RuntimeError(f"tiles {tuple(tiles.shape)} do not match {n_images} images of {nV}x{nH} patches")
+    dev = tiles.device
+    if weights is not None:
+        _lib.require_cuda(weights, "weights", torch.float32)
+        assert tuple(weights.shape) == (K, K)
+    if black is not None:
+        _lib.require_cuda(black, "black", torch.uint8)
+    if out is None:
+        out = torch.empty(n_images, nV * inner, nH * inner, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mrinr_patches_to_image(tiles.data_ptr(), _ptr(weights), _ptr(black), n_images, nV, nH, K, inner,
+                                              out.data_ptr(), _lib.stream_ptr(dev)), "patches_to_image")
+    return out
+
+
+def complex_abs(data: torch.Tensor) -> torch.Tensor:
+    """``fastmri.complex_abs`` as used at src/data/preprocessing.py:58: ``[...,2]`` -> ``[...]``."""
+    lib = _lib.load()
+    _lib.require_cuda(data, "data", torch.float32)
+    if data.shape[-1] != 2:
+        raise RuntimeError("last dimension must be 2 (real, imag)")
+    out = torch.empty(data.shape[:-1], dtype=torch.float32, device=data.device)
+    with torch.cuda.device(data.device):
+        _lib.check(lib.mrinr_complex_abs(data.data_ptr(), out.numel(), out.data_ptr(), _lib.stream_ptr(data.device)),
+                   "complex_abs")
+    return out
+
+
+def minmax_normalize(x: torch.Tensor, groups: int = 1) -> torch.Tensor:
+    """``normalize_scan`` (src/util/visualization.py:113-126): per group ``(x-min)/(max-min)``; ``x`` is
+    viewed as ``[groups, -1]`` (one group = one image or one volume, preprocessing.py:127-137)."""
+    lib = _lib.load()
+    _lib.require_cuda(x, "x", torch.float32)
+    n = x.numel() // max(groups, 1)
+    out = torch.empty_like(x)
+    scratch = torch.empty(2 * max(groups, 1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mrinr_minmax_normalize(x.data_ptr(), groups, n, out.data_ptr(), scratch.data_ptr(),
+                                              _lib.stream_ptr(x.device)), "minmax_normalize")
+    return out

@@ -1,0 +1,264 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors of the
+unmodified reference.  Bit-exact for indices / grids / reassembly; floating-point tolerances are stated inline.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import siren as osiren
+from oracle import tiling as otiling
+from oracle.synth import MODEL_CASES, synth_image, synth_tiles
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _model(sd_kw, act, model_kw, precision):
+    from mri_inr_b200.modulated_siren import ModulatedSiren
+
+    sd = osiren.synth_state_dict(**sd_kw)
+    m = ModulatedSiren(dim_in=2, dim_hidden=256, dim_out=1, num_layers=model_kw.get("num_layers", 5),
+                       latent_dim=model_kw.get("latent_dim", 256), w0=model_kw.get("w0", 1.0), w0_initial=30.0,
+                       use_bias=model_kw.get("use_bias", True), dropout=0.1, modulate=True, encoder_type="custom",
+                       encoder_path=None, outer_patch_size=32, inner_patch_size=16, siren_patch_size=24,
+                       device=torch.device("cpu"), activation=act)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.to(DEV).eval()
+    m.precision = precision
+    return m, sd
+
+
+# ---------------------------------------------------------------------------------------------- grid
+@pytest.mark.parametrize("s", [8, 16, 24, 32, 48])
+def test_make_grid_bit_exact(golden, s):
+    from mri_inr_b200 import ops
+
+    g = ops.make_grid(s, DEV).cpu().numpy()
+    assert np.array_equal(g.view(np.uint32), golden["grid_weights"][f"grid_{s}"].view(np.uint32))
+    assert np.array_equal(g.view(np.uint32), osiren.make_grid(s).view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------- tiling
+@pytest.mark.parametrize("tag,hw", [("a", (50, 37)), ("b", (64, 48)), ("c", (320, 320))])
+def test_tiling_bit_exact(golden, tag, hw):
+    from mri_inr_b200 import tiling
+
+    g = golden["tiling"]
+    h, w = hw
+    img = synth_image(7 + h, h, w)
+    t = torch.from_numpy(img)[None].to(DEV)
+    patches, info = tiling.image_to_patches(t, 32, 16)
+    assert tuple(info[0]) == tuple(g[f"{tag}_info"])
+    ref_patches, _ = otiling.image_to_patches(img[None], 32, 16)
+    assert np.array_equal(patches.cpu().numpy(), ref_patches)            # indices bit-exact
+    if tag != "c":
+        assert np.array_equal(patches.cpu().numpy(), g[f"{tag}_patches"])
+    kept, black, shape = tiling.filter_and_remember_black_patches(patches)
+    assert black == list(g[f"{tag}_black"])
+    assert kept.shape[0] == patches.shape[0] - len(black)
+    rs = np.random.RandomState(h * w)
+    small = torch.from_numpy(rs.uniform(-1, 1, size=(patches.shape[0], 24, 24)).astype(np.float32)).to(DEV)
+    keep = np.ones(patches.shape[0], bool)
+    keep[black] = False
+    reint = tiling.reintegrate_black_patches(small[torch.from_numpy(keep).to(DEV)], black, shape)
+    wavg = tiling.patches_to_image_weighted_average(reint, info, 24, 16, DEV)
+    plain = tiling.patches_to_image(patches, info, 32, 16)
+    # same accumulation order as F.fold on CPU -> bit-exact against the reference's own output
+    assert np.array_equal(wavg.cpu().numpy().view(np.uint32), g[f"{tag}_wavg"].view(np.uint32))
+    assert np.array_equal(plain.cpu().numpy().view(np.uint32), g[f"{tag}_plain"].view(np.uint32))
+
+
+def test_weight_matrix_bit_exact(golden):
+    from mri_inr_b200 import tiling
+
+    for k in (16, 24, 32):
+        w = tiling.generate_weight_matrix(k).numpy()
+        assert np.array_equal(w.view(np.uint32), golden["grid_weights"][f"weights_{k}"].view(np.uint32))
+
+
+def test_batched_tiling_and_black_mask():
+    from mri_inr_b200 import ops
+
+    imgs = np.stack([synth_image(i, 96, 80) for i in range(5)])
+    imgs[3] = 0.0
+    t = torch.from_numpy(imgs).to(DEV)
+    patches, (nv, nh), black = ops.image_to_patches(t, 32, 16, with_black_mask=True)
+    ref, info = otiling.image_to_patches(imgs, 32, 16)
+    assert (nv, nh) == info[0]
+    assert np.array_equal(patches.cpu().numpy(), ref)
+    assert np.array_equal(black.cpu().numpy().astype(bool), otiling.black_mask(ref))
+    assert black[3 * nv * nh:4 * nv * nh].all()
+    # reassembly of the extracted patches gives the image back (unit weights: every pixel is an average of copies)
+    back = ops.patches_to_image(patches, 5, (nv, nh), 16)
+    np.testing.assert_allclose(back.cpu().numpy(), imgs, rtol=0, atol=1e-6)
+    # empty batch
+    e, _, _ = ops.image_to_patches(t[:0], 32, 16)
+    assert e.shape[0] == 0
+
+
+def test_complex_abs_and_normalize(golden):
+    from mri_inr_b200 import ops
+
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.normal(size=(7, 33, 2)).astype(np.float32))
+    want = (x ** 2).sum(dim=-1).sqrt()
+    got = ops.complex_abs(x.to(DEV)).cpu()
+    assert torch.equal(got, want)
+    y = torch.from_numpy(np.random.RandomState(5).normal(size=(3, 40, 40)).astype(np.float32))
+    assert np.array_equal(ops.minmax_normalize(y.to(DEV)).cpu().numpy(), golden["normalize"]["out"])
+    per = ops.minmax_normalize(y.to(DEV), groups=3).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(per[i], otiling.normalize_scan(y[i].numpy()))
+
+
+# ---------------------------------------------------------------------------------------------- model
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
+def test_modulator_matches_reference(golden, case):
+    name, sd_kw, act, model_kw = case
+    m, sd = _model(sd_kw, act, model_kw, "fp32")
+    g = golden["model_forward"]
+    z = torch.from_numpy(g[f"{name}_latent"]).to(DEV)
+    with torch.no_grad():
+        mods = torch.stack(list(m.modulator(z))).cpu().numpy()
+    np.testing.assert_allclose(mods, g[f"{name}_mods"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
+def test_layer0_table(case):
+    name, sd_kw, act, model_kw = case
+    m, sd = _model(sd_kw, act, model_kw, "fp32")
+    tab = m._packed().layer0_table().cpu()
+    pre = torch.nn.functional.linear(sd["grid"], sd["net.layers.0.weight"], sd.get("net.layers.0.bias"))
+    want = osiren._activation(pre, 30.0, act)
+    # |30*pre| reaches ~45 rad: 1 ulp of the argument is 4e-6
+    np.testing.assert_allclose(tab.numpy(), want.numpy(), rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16", 1e-3)])
+def test_forward_matches_reference(golden, case, precision, tol):
+    """forward(tiles) against the reference's own output (golden) -- north_star tolerance: max-abs 1e-3."""
+    name, sd_kw, act, model_kw = case
+    m, sd = _model(sd_kw, act, model_kw, precision)
+    tiles = torch.from_numpy(synth_tiles(100 + sd_kw["seed"], 5)).to(DEV)
+    with torch.no_grad():
+        y = m(tiles)
+    assert y.shape == (5, 24, 24) and y.dtype == torch.float32
+    err = np.abs(y.cpu().numpy() - golden["model_forward"][f"{name}_out"]).max()
+    print(f"{name} {precision}: max-abs err {err:.3e}")
+    assert err <= tol
+
+
+def test_forward_bf16_random_init(golden):
+    name, sd_kw, act, model_kw = MODEL_CASES[0]
+    m, sd = _model(sd_kw, act, model_kw, "bf16")
+    tiles = torch.from_numpy(synth_tiles(100 + sd_kw["seed"], 5)).to(DEV)
+    with torch.no_grad():
+        y = m(tiles)
+    err = np.abs(y.cpu().numpy() - golden["model_forward"][f"{name}_out"]).max()
+    assert err <= 1e-3
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16", 1e-3)])
+@pytest.mark.parametrize("B", [1, 2, 223, 400])
+def test_forward_matches_oracle_ragged_batches(precision, tol, B):
+    """B*576 is not a multiple of the 128-row tile for most B: tiles straddle patches and the last tile is ragged."""
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, precision)
+    tiles_np = synth_tiles(B, B)
+    with torch.no_grad():
+        y = m(torch.from_numpy(tiles_np).to(DEV)).cpu().numpy()
+    want = osiren.model_forward(sd, torch.from_numpy(tiles_np), activation=act).numpy()
+    err = np.abs(y - want).max()
+    print(f"B={B} {precision}: max-abs err {err:.3e}")
+    assert err <= tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_reduced_latent_residual_shape(precision):
+    """BASELINE config 4 (builder-defined): L=9, latent 128.  Oracle-only parity (the reference's
+    custom encoder is hard-wired to a 256-d latent)."""
+    sd_kw = dict(seed=21, num_layers=9, latent_dim=128, mod_bias_shift=0.25)
+    m, sd = _model(sd_kw, "sine", dict(num_layers=9, latent_dim=128), precision)
+    tiles_np = synth_tiles(77, 9)
+    with torch.no_grad():
+        y = m(torch.from_numpy(tiles_np).to(DEV)).cpu().numpy()
+    want = osiren.model_forward(sd, torch.from_numpy(tiles_np), num_layers=9).numpy()
+    assert np.abs(y - want).max() <= (2e-5 if precision == "fp32" else 1e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_black_patches_are_skipped_and_zero(precision):
+    from mri_inr_b200 import ops
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, precision)
+    B = 37
+    tiles_np = synth_tiles(5, B)
+    black_idx = [0, 1, 5, 6, 7, 20, 36]
+    tiles_np[black_idx] = 0.0
+    tiles = torch.from_numpy(tiles_np).to(DEV)
+    with torch.no_grad():
+        mods = m.modulations(tiles)
+        black = ops.classify_patches(tiles)
+        assert black.cpu().nonzero().flatten().tolist() == black_idx
+        y = m.synthesize(mods, black=black).cpu().numpy()
+        y_all = m.synthesize(mods).cpu().numpy()
+    assert np.all(y[black_idx] == 0)
+    keep = [i for i in range(B) if i not in black_idx]
+    assert np.array_equal(y[keep], y_all[keep])          # compaction does not change the arithmetic
+    # all black / none black
+    with torch.no_grad():
+        allb = m.synthesize(mods, black=torch.ones(B, dtype=torch.uint8, device=DEV)).cpu().numpy()
+    assert np.all(allb == 0)
+
+
+def test_pipeline_matches_reference_flow():
+    """Body of metrics_error (error.py:230-248): filter black -> model -> reintegrate -> weighted fold."""
+    from mri_inr_b200.pipeline import ReconstructionPipeline
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    imgs = np.stack([synth_image(40 + i, 96, 112) for i in range(3)])
+    pipe = ReconstructionPipeline(m, chunk_slices=2)
+    rec = pipe.reconstruct(torch.from_numpy(imgs).to(DEV)).cpu().numpy()
+    for i in range(3):
+        patches, info = otiling.image_to_patches(imgs[i:i + 1], 32, 16)
+        kept, black, shape = otiling.filter_and_remember_black_patches(patches)
+        out = osiren.model_forward(sd, torch.from_numpy(kept), activation=act).numpy()
+        full = otiling.reintegrate_black_patches(out, black, shape)
+        want = otiling.patches_to_image_weighted_average(full, info, 24, 16)[0]
+        assert len(black) > 0
+        assert np.abs(rec[i] - want).max() <= 1e-3
+
+
+def test_cpu_tensors_and_grad_are_refused():
+    name, sd_kw, act, model_kw = MODEL_CASES[0]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        m(torch.zeros(2, 32, 32))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 32, 32, device=DEV))          # grad enabled
+
+
+def test_full_size_properties():
+    """At BASELINE size (a 320x320 slice = 400 patches, 230 400 coords): size-independent properties.
+    (1) evaluation is per patch: permuting the batch permutes the output; (2) duplicate patches give
+    bit-identical outputs regardless of their position in the tile stream; (3) |y| <= 1."""
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    img = synth_image(99, 320, 320)
+    from mri_inr_b200 import ops
+
+    patches, _, _ = ops.image_to_patches(torch.from_numpy(img)[None].to(DEV), 32, 16)
+    assert patches.shape[0] == 400
+    perm = torch.from_numpy(np.random.RandomState(0).permutation(400)).to(DEV)
+    with torch.no_grad():
+        y = m(patches)
+        yp = m(patches[perm])
+        dup = m(torch.cat([patches[7:8]] * 5 + [patches[:3]]))
+    assert torch.equal(yp, y[perm])
+    assert all(torch.equal(dup[0], dup[i]) for i in range(1, 5))
+    assert float(y.abs().max()) <= 1.0

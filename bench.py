@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): reconstructed 320x320 slices/s of the modulated-SIREN inference path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--activation sine|morlet]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+
+Workload (config[1] of BASELINE.json): baseline modulated SIREN, random-init weights (reference init ranges),
+batched inference over a synthetic 940-volume-shaped validation set = 940 volumes x 11 slices = 10 340 slices of
+320x320 (acc 6 / cf 0.05 synthetic single-coil k-space).  One step = one pass over the whole set.  With N GPUs the
+set is block-partitioned by slice over the ranks (strong scaling) and the reconstructed slices are gathered to
+rank 0 with point-to-point NCCL transfers inside the timed region.
+
+`value`: slices/s with the inputs resident in HBM.  `e2e`: the same pass through the public pipeline from pinned
+HOST buffers (H2D of the undersampled slices and D2H of the reconstructions inside the timed region).
+`roofline`: the fused tcgen05 synthesis kernel, timed with CUDA events around every launch in the timed region.
+`cpu_baseline` / `--impl reference`: the reference's own CPU op sequence (oracle/flow.py; the reference is pure
+Python and /root/reference does not exist on the GPU box, so the port is timed: kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_VOLUMES, SLICES_PER_VOLUME, IMG = 940, 11, 320
+N_SLICES = N_VOLUMES * SLICES_PER_VOLUME                 # 10 340
+PATCHES_PER_SLICE, COORDS_PER_PATCH = 400, 576
+FLOP_PER_COORD = 4 * 2 * 256 * 256                       # tensor-eligible hidden contractions
+METRIC = "reconstructed 320x320 slices/sec"
+MODEL_KW = dict(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=1.0, w0_initial=30.0,
+                use_bias=True, dropout=0.1, modulate=True, encoder_type="custom", encoder_path=None,
+                outer_patch_size=32, inner_patch_size=16, siren_patch_size=24)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_state_dict(activation: str, seed: int = 0):
+    """Random-init weights of the baseline architecture with the reference's init ranges
+    (Siren.init_, modulated_siren.py:126-142; nn.Linear / nn.Conv2d defaults)."""
+    import torch
+
+    from mri_inr_b200.modulated_siren import ModulatedSiren
+
+    torch.manual_seed(seed)
+    model = ModulatedSiren(device=torch.device("cpu"), activation=activation, **MODEL_KW)
+    return model, {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def cpu_reference_rate(sd, slices_cpu, activation, n_warm=1, budget_s=20.0, max_slices=24):
+    """slices/s of the reference's CPU op sequence (oracle/flow.py) on a bounded sample, all host threads."""
+    import torch
+
+    from oracle import flow
+
+    for i in range(n_warm):
+        flow.reconstruct_slice(sd, slices_cpu[i % len(slices_cpu)], activation=activation)
+    t0, n = time.perf_counter(), 0
+    while n < max_slices and (n < 2 or time.perf_counter() - t0 < budget_s):
+        flow.reconstruct_slice(sd, slices_cpu[n % len(slices_cpu)], activation=activation)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, n, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (port, see module docstring)."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mri_inr_b200.synthetic import column_mask  # noqa: F401  (host-only helper; no GPU needed here)
+    import numpy as np
+
+    _, sd = build_state_dict(args.activation)
+    # the same kind of input as the GPU arm, generated on the host (no GPU work in this arm)
+    rs = np.random.RandomState(1234)
+    sample = max(1, args.ref_slices)
+    slices = []
+    yy, xx = np.meshgrid(np.linspace(-1, 1, IMG), np.linspace(-1, 1, IMG), indexing="ij")
+    mask = column_mask(IMG, 6, 0.05, 1234)
+    for i in range(sample):
+        field = rs.uniform(size=(IMG, IMG))
+        f = np.fft.fft2(field) * np.exp(-(np.fft.fftfreq(IMG)[:, None] ** 2 + np.fft.fftfreq(IMG)[None, :] ** 2) / (2 * 0.03 ** 2))
+        ph = (np.fft.ifft2(f).real - np.fft.ifft2(f).real.min()) * ((xx / 0.7) ** 2 + (yy / 0.8) ** 2 <= 1)
+        k = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(ph), norm="ortho")) * mask
+        im = np.abs(np.fft.fftshift(np.fft.ifft2(np.fft.ifftshift(k), norm="ortho")))
+        im = (im - im.min()) / (im.max() - im.min())
+        slices.append(torch.from_numpy(im.astype(np.float32)))
+    from oracle import flow
+
+    for _ in range(args.warmup):
+        flow.reconstruct_slice(sd, slices[0], activation=args.activation)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for s in slices:
+            flow.reconstruct_slice(sd, s, activation=args.activation)
+    dt = time.perf_counter() - t0
+    rate = args.steps * sample / dt
+    threads = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "slices/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"baseline modulated SIREN ({args.activation}) inference, {N_SLICES} synthetic 320x320 "
+                               f"slices (940 volumes x 11); CPU arm times a bounded sample of {sample} slice(s) per step",
+                   "coords_per_s": rate * PATCHES_PER_SLICE * COORDS_PER_PATCH},
+        "cpu_baseline": {"value": rate, "unit": "slices/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} slice(s)/step x {args.steps} steps, torch {torch.__version__} CPU, "
+                                   f"{threads} threads of {os.cpu_count()} cpus"},
+        "e2e": {"value": rate, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mri_inr_b200 import _lib
+    from mri_inr_b200.dist import gather_slices, shard_range
+    from mri_inr_b200.pipeline import ReconstructionPipeline
+    from mri_inr_b200.synthetic import synthetic_slices
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_total = args.slices
+    s0, s1 = shard_range(n_total, rank, world)
+    n_local = s1 - s0
+
+    model, sd = build_state_dict(args.activation)
+    model.to(dev).eval()
+    model.precision = args.precision
+    pipe = ReconstructionPipeline(model, chunk_slices=args.chunk)
+
+    # synthetic undersampled slices of this rank's block (set-up, untimed); seeds depend on the global index
+    images = synthetic_slices(n_local, IMG, IMG, device=dev, seed=1234 + s0)
+    recon = torch.empty(n_local, IMG, IMG, dtype=torch.float32, device=dev)
+    gathered = torch.empty(n_total, IMG, IMG, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    black_frac = float((images.reshape(n_local, -1).amax(dim=1) == 0).float().mean()) if n_local else 0.0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(events=None):
+        pipe.reconstruct(images, out=recon, kernel_events=events)
+        if world > 1:
+            gather_slices(recon, n_total, dst=0, out=gathered)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    events = []
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(events)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in events)
+    kern_patches = sum(n for _, _, n in events)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = args.steps * n_total / (ms_total * 1e-3)
+
+    # ---- end to end: pinned host -> device -> pipeline -> pinned host, every step
+    # (every rank uploads its block; the reconstructed set lands in host memory of rank 0)
+    host_in = torch.empty(n_local, IMG, IMG, dtype=torch.float32).pin_memory()
+    host_out = torch.empty(n_total if rank == 0 else 1, IMG, IMG, dtype=torch.float32).pin_memory()
+    host_in.copy_(images)
+    dev_in = torch.empty_like(images)
+
+    def e2e_step():
+        dev_in.copy_(host_in, non_blocking=True)
+        pipe.reconstruct(dev_in, out=recon)
+        if world > 1:
+            gather_slices(recon, n_total, dst=0, out=gathered)
+            if rank == 0:
+                host_out.copy_(gathered, non_blocking=True)
+        else:
+            host_out.copy_(recon, non_blocking=True)
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * n_total / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        achieved = (kern_patches * COORDS_PER_PATCH * FLOP_PER_COORD) / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, n, threads = cpu_reference_rate(sd, [images[i].cpu() for i in range(min(4, n_local))], args.activation)
+            cpu = {"value": rate, "unit": "slices/s", "cores": threads, "kind": "port",
+                   "sample": f"{n} slices of the same workload through oracle/flow.py (reference op sequence), "
+                             f"{threads} torch threads of {os.cpu_count()} cpus"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else args.precision,
+            "data": "synthetic",
+            "config": {"workload": f"baseline modulated SIREN ({args.activation}) batched inference over a synthetic "
+                                   f"940-volume-shaped set: {n_total} slices 320x320 (acc 6 / cf 0.05), random-init "
+                                   f"weights; patches -> encoder -> modulator -> fused tcgen05 MLP -> weighted reassembly",
+                       "slices": n_total, "chunk_slices": args.chunk, "parallelism": f"slices block-partitioned x{world}",
+                       "precision": f"{args.precision} operands, fp32 accumulate", "black_patch_fraction": black_frac,
+                       "coords_per_s": value * PATCHES_PER_SLICE * COORDS_PER_PATCH,
+                       "l2": f"inputs larger than L2 ({n_local * IMG * IMG * 4 / 1e6:.0f} MB of slices per rank per step; "
+                             f"intermediates {args.chunk * 400 * (1024 + 5 * 256 + 576) * 4 / 1e6:.0f} MB per chunk)"},
+            "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": n_total * IMG * IMG * 4,
+                    "d2h_bytes_per_step": n_total * IMG * IMG * 4, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "kernel": "siren_tc_kernel (fused modulated-SIREN MLP)", "peak_source": f"{peak_src}, sustained bf16",
+                         "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
+                         "kernel_ms_per_step": kern_ms / args.steps, "kernel_launches_timed": len(events),
+                         "kernel_share_of_step": kern_ms / ms_total},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--activation", default="sine", choices=["sine", "morlet"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--slices", type=int, default=N_SLICES)
+    ap.add_argument("--chunk", type=int, default=235)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-slices", type=int, default=4, help="slices per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

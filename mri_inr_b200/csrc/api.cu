@@ -190,6 +190,7 @@ extern "C" int64_t mrinr_siren_workspace_bytes(int64_t B) {
 
 extern "C" int mrinr_siren_forward(const MrinrPacked* p, const float* d_mods, const uint8_t* d_black, int64_t B,
                                    float* d_out, void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;
   MRINR_REQUIRE(p && d_mods && d_out, MRINR_E_ARG, "mrinr_siren_forward: null pointer");
   MRINR_REQUIRE(B >= 0 && B * (int64_t)p->C < ((int64_t)1 << 40), MRINR_E_ARG, "mrinr_siren_forward: bad batch %lld",
                 (long long)B);

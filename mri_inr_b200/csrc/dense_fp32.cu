@@ -234,6 +234,7 @@ using namespace mrinr;
 
 extern "C" int mrinr_modulator_forward(const MrinrPacked* p, const float* d_latent, int64_t B, float* d_mods,
                                        void* stream) {
+  if (B == 0) return 0;
   MRINR_REQUIRE(p && d_latent && d_mods, MRINR_E_ARG, "mrinr_modulator_forward: null pointer");
   MRINR_REQUIRE(B >= 0, MRINR_E_ARG, "mrinr_modulator_forward: negative batch");
   if (B == 0) return 0;

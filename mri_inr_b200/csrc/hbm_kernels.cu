@@ -348,6 +348,7 @@ extern "C" int mrinr_make_grid(int32_t S, float* d_out, void* stream) {
 
 extern "C" int mrinr_image_to_patches(const float* d_img, int64_t N, int32_t H, int32_t W, int32_t O, int32_t I,
                                       float* d_patches, uint8_t* d_black, void* stream) {
+  if (N == 0) return 0;
   MRINR_REQUIRE(d_img && d_patches, MRINR_E_ARG, "mrinr_image_to_patches: null pointer");
   MRINR_REQUIRE(N >= 0 && H > 0 && W > 0 && O > 0 && I > 0, MRINR_E_ARG, "mrinr_image_to_patches: bad sizes");
   MRINR_REQUIRE(O >= I && ((O - I) % 2) == 0 && (O % 4) == 0, MRINR_E_UNSUPPORTED,
@@ -371,8 +372,8 @@ extern "C" int mrinr_image_to_patches(const float* d_img, int64_t N, int32_t H, 
 
 extern "C" int mrinr_classify_patches(const float* d_patches, int64_t n_patches, int32_t elems, uint8_t* d_black,
                                       void* stream) {
-  MRINR_REQUIRE(d_patches && d_black && n_patches >= 0 && elems > 0, MRINR_E_ARG, "mrinr_classify_patches: bad arguments");
   if (n_patches == 0) return 0;
+  MRINR_REQUIRE(d_patches && d_black && n_patches >= 0 && elems > 0, MRINR_E_ARG, "mrinr_classify_patches: bad arguments");
   const long long threads = (long long)n_patches * 32;
   classify_patches_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_patches, n_patches,
                                                                                              elems, d_black);
@@ -383,6 +384,7 @@ extern "C" int mrinr_classify_patches(const float* d_patches, int64_t n_patches,
 extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weights, const uint8_t* d_black,
                                       int64_t N, int32_t nV, int32_t nH, int32_t K, int32_t I, float* d_img,
                                       void* stream) {
+  if (N == 0) return 0;
   MRINR_REQUIRE(d_tiles && d_img, MRINR_E_ARG, "mrinr_patches_to_image: null pointer");
   MRINR_REQUIRE(N >= 0 && nV > 0 && nH > 0 && K > 0 && I > 0 && K >= I && ((K - I) % 2) == 0, MRINR_E_ARG,
                 "mrinr_patches_to_image: bad sizes (K=%d I=%d)", K, I);
@@ -395,8 +397,8 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
 }
 
 extern "C" int mrinr_complex_abs(const float* d_in, int64_t n, float* d_out, void* stream) {
-  MRINR_REQUIRE(d_in && d_out && n >= 0, MRINR_E_ARG, "mrinr_complex_abs: bad arguments");
   if (n == 0) return 0;
+  MRINR_REQUIRE(d_in && d_out && n >= 0, MRINR_E_ARG, "mrinr_complex_abs: bad arguments");
   complex_abs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float2*>(d_in), n, d_out);
   count_launch();

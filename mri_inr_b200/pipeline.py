@@ -39,8 +39,11 @@ class ReconstructionPipeline:
 
     @torch.no_grad()
     def reconstruct(self, images: torch.Tensor, out: Optional[torch.Tensor] = None,
-                    skip_black: bool = True) -> torch.Tensor:
-        """``images [N,H,W]`` (undersampled, fp32, CUDA) -> reconstructed ``[N, nV*I, nH*I]``."""
+                    skip_black: bool = True, kernel_events: Optional[list] = None) -> torch.Tensor:
+        """``images [N,H,W]`` (undersampled, fp32, CUDA) -> reconstructed ``[N, nV*I, nH*I]``.
+
+        ``kernel_events``: if a list is given, a ``(start, end, n_patches)`` CUDA-event pair bracketing every
+        synthesis-kernel launch is appended (recorded on the launching stream; used by bench.py's roofline)."""
         m = self.model
         m._check_inference()
         if images.dim() != 3 or not images.is_cuda:
@@ -67,6 +70,12 @@ class ReconstructionPipeline:
                                                      out=patches_buf[:B])
             z = m.encoder(patches)
             mods = ops.modulator_forward(packed, z.contiguous(), out=mods_buf[: packed.L * B * packed.H].view(packed.L, B, packed.H))
+            if kernel_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             tiles = ops.siren_forward(packed, mods, black=black, out=tiles_buf[:B], workspace=ws_buf)
+            if kernel_events is not None:
+                e1.record()
+                kernel_events.append((e0, e1, B))
             ops.patches_to_image(tiles.view(B, S, S), n, (nV, nH), I, weights=wts, black=black, out=out[s0:s0 + n])
         return out

@@ -105,12 +105,16 @@ def test_complex_abs_and_normalize(golden):
     x = torch.from_numpy(rs.normal(size=(7, 33, 2)).astype(np.float32))
     want = (x ** 2).sum(dim=-1).sqrt()
     got = ops.complex_abs(x.to(DEV)).cpu()
-    assert torch.equal(got, want)
+    assert got.shape == want.shape
+    assert torch.equal(got, want), f"complex_abs max diff {float((got - want).abs().max()):.3e}"
     y = torch.from_numpy(np.random.RandomState(5).normal(size=(3, 40, 40)).astype(np.float32))
-    assert np.array_equal(ops.minmax_normalize(y.to(DEV)).cpu().numpy(), golden["normalize"]["out"])
+    whole = ops.minmax_normalize(y.to(DEV)).cpu().numpy()
+    assert np.array_equal(whole, golden["normalize"]["out"]), \
+        f"normalize max diff {np.abs(whole - golden['normalize']['out']).max():.3e}"
     per = ops.minmax_normalize(y.to(DEV), groups=3).cpu().numpy()
     for i in range(3):
-        assert np.array_equal(per[i], otiling.normalize_scan(y[i].numpy()))
+        want_i = otiling.normalize_scan(y[i].numpy())
+        assert np.array_equal(per[i], want_i), f"group {i} max diff {np.abs(per[i] - want_i).max():.3e}"
 
 
 # ---------------------------------------------------------------------------------------------- model
@@ -244,9 +248,10 @@ def test_cpu_tensors_and_grad_are_refused():
 
 
 def test_full_size_properties():
-    """At BASELINE size (a 320x320 slice = 400 patches, 230 400 coords): size-independent properties.
-    (1) evaluation is per patch: permuting the batch permutes the output; (2) duplicate patches give
-    bit-identical outputs regardless of their position in the tile stream; (3) |y| <= 1."""
+    """At BASELINE size (a 320x320 slice = 400 patches, 230 400 coords): size-independent properties of the
+    synthesis kernel.  (1) evaluation is per patch: permuting the modulations permutes the output bit for bit;
+    (2) duplicate patches give bit-identical outputs wherever they sit in the 128-row tile stream;
+    (3) |y| <= 1; (4) the batched forward equals the oracle within the north_star tolerance."""
     name, sd_kw, act, model_kw = MODEL_CASES[1]
     m, sd = _model(sd_kw, act, model_kw, "fp16")
     img = synth_image(99, 320, 320)
@@ -256,9 +261,14 @@ def test_full_size_properties():
     assert patches.shape[0] == 400
     perm = torch.from_numpy(np.random.RandomState(0).permutation(400)).to(DEV)
     with torch.no_grad():
-        y = m(patches)
-        yp = m(patches[perm])
-        dup = m(torch.cat([patches[7:8]] * 5 + [patches[:3]]))
+        mods = m.modulations(patches)
+        y = m.synthesize(mods)
+        yp = m.synthesize(mods[:, perm].contiguous())
+        dup_idx = torch.tensor([7] * 5 + [0, 1, 2], device=DEV)
+        dup = m.synthesize(mods[:, dup_idx].contiguous())
     assert torch.equal(yp, y[perm])
     assert all(torch.equal(dup[0], dup[i]) for i in range(1, 5))
+    assert torch.equal(dup[0], y[7])
     assert float(y.abs().max()) <= 1.0
+    want = osiren.model_forward(sd, patches.cpu(), activation=act).numpy()
+    assert np.abs(y.cpu().numpy() - want).max() <= 1e-3

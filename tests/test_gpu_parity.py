@@ -106,7 +106,12 @@ def test_complex_abs_and_normalize(golden):
     want = (x ** 2).sum(dim=-1).sqrt()
     got = ops.complex_abs(x.to(DEV)).cpu()
     assert got.shape == want.shape
-    assert torch.equal(got, want), f"complex_abs max diff {float((got - want).abs().max()):.3e}"
+    # the kernel is correctly rounded (IEEE sqrt of separately rounded squares) == numpy; torch's vectorised CPU
+    # sqrt differs from IEEE by 1 ulp on some inputs, so the torch comparison allows 1 ulp
+    xn = x.numpy()
+    ieee = np.sqrt(xn[..., 0] * xn[..., 0] + xn[..., 1] * xn[..., 1])
+    assert np.array_equal(got.numpy(), ieee)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1.2e-7, atol=0)
     y = torch.from_numpy(np.random.RandomState(5).normal(size=(3, 40, 40)).astype(np.float32))
     whole = ops.minmax_normalize(y.to(DEV)).cpu().numpy()
     assert np.array_equal(whole, golden["normalize"]["out"]), \

@@ -45,6 +45,9 @@ extern "C" void mrinr_free_packed(MrinrPacked* p) {
   cudaFree(p->d_table0);
   cudaFree(p->d_net_wT);
   cudaFree(p->d_net_w16);
+  cudaFree(p->d_net_w16p);
+  cudaFree(p->d_layer0);
+  cudaFree(p->d_grid);
   cudaFree(p->d_net_bias);
   cudaFree(p->d_last_w);
   cudaFree(p->d_last_b);
@@ -125,6 +128,9 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     PK_CUDA(cudaMalloc(&p->d_table0, (size_t)C * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_wT, (size_t)(L - 1) * H * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_w16, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
+    PK_CUDA(cudaMalloc(&p->d_net_w16p, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
+    PK_CUDA(cudaMalloc(&p->d_layer0, (size_t)3 * H * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_grid, (size_t)C * 2 * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_bias, (size_t)L * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_last_w, (size_t)H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_last_b, sizeof(float)));
@@ -136,6 +142,14 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     PK_CUDA(cudaMemsetAsync(p->d_last_b, 0, sizeof(float), st));
 
     const float* b0 = (v->d_net_bias && v->d_net_bias[0]) ? v->d_net_bias[0] : nullptr;
+    // layer-0 parameters as three [H] rows: W_0[:,0], W_0[:,1], b_0
+    PK_CUDA(cudaMemsetAsync(p->d_layer0, 0, (size_t)3 * H * sizeof(float), st));
+    PK_CUDA(cudaMemcpy2DAsync(p->d_layer0, sizeof(float), v->d_net_weight[0], 2 * sizeof(float), sizeof(float), H,
+                              cudaMemcpyDeviceToDevice, st));
+    PK_CUDA(cudaMemcpy2DAsync(p->d_layer0 + H, sizeof(float), v->d_net_weight[0] + 1, 2 * sizeof(float), sizeof(float), H,
+                              cudaMemcpyDeviceToDevice, st));
+    if (b0) PK_CUDA(cudaMemcpyAsync(p->d_layer0 + 2 * H, b0, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->d_grid, v->d_grid, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PK_RC(run_layer0_table(v->d_grid, v->d_net_weight[0], b0, C, H, p->w0_initial, p->activation, p->d_table0, st));
     for (int l = 0; l < L; ++l) {
       if (v->d_net_bias && v->d_net_bias[l])
@@ -146,9 +160,12 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     }
     for (int l = 1; l < L; ++l) {
       PK_RC(run_transpose(v->d_net_weight[l], H, H, p->d_net_wT + (size_t)(l - 1) * H * H, st));
-      if (precision != MRINR_PREC_FP32)
+      if (precision != MRINR_PREC_FP32) {
         PK_RC(run_pack_w16(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
                            p->d_net_w16 + (size_t)(l - 1) * H * H, st));
+        PK_RC(run_pack_w16_pair(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
+                                p->d_net_w16p + (size_t)(l - 1) * H * H, st));
+      }
     }
     PK_CUDA(cudaMemcpyAsync(p->d_last_w, v->d_last_weight, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (v->d_last_bias)

@@ -41,6 +41,28 @@ __global__ void pack_w16_kernel(const float* __restrict__ w, int H, int use_bf16
   out[i] = bits;
 }
 
+// cta_group::2 variant: CTA rank r of a pair holds output rows n in [128r, 128r+128) of every layer:
+// out[r][kc][n'][e] = cvt(W[128r + n'][8*kc + e]).  A K=64 slab of one rank is 16 KB contiguous.
+__global__ void pack_w16_pair_kernel(const float* __restrict__ w, int H, int use_bf16, uint16_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * H) return;
+  const int half_rows = H / 2;
+  const int e = i & 7;
+  const int np = (i >> 3) % half_rows;
+  const int kc = ((i >> 3) / half_rows) % (H / 8);
+  const int r = (i >> 3) / half_rows / (H / 8);
+  const float v = w[(long long)(r * half_rows + np) * H + kc * 8 + e];
+  uint16_t bits;
+  if (use_bf16) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&b);
+  } else {
+    const __half h = __float2half_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&h);
+  }
+  out[i] = bits;
+}
+
 __device__ __forceinline__ float act_exact(float pre, float w0, int activation) {
   // Sine: modulated_siren.py:54 ; Morlet: :80 (Gaussian on the un-scaled pre-activation)
   const float s = sinf(w0 * pre);
@@ -200,6 +222,12 @@ int run_pack_w16(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_
   pack_w16_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(w, H, use_bf16, out);
   count_launch();
   return check_launch("pack_w16");
+}
+
+int run_pack_w16_pair(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_t st) {
+  pack_w16_pair_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(w, H, use_bf16, out);
+  count_launch();
+  return check_launch("pack_w16_pair");
 }
 
 int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,

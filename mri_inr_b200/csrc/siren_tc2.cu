@@ -359,15 +359,4 @@ int launch_siren_tc_v2(const MrinrPacked* p, const float* d_mods, const int32_t*
 
 }  // namespace v2
 
-int launch_siren_tc(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
-                    int64_t B, float* d_out, cudaStream_t st) {
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("MRINR_TC_VARIANT");
-    variant = (e && e[0] == '1') ? 1 : 2;
-  }
-  if (variant == 1 || p->L < 3) return v1::launch_siren_tc_v1(p, d_mods, d_idx, d_nactive, B, d_out, st);
-  return v2::launch_siren_tc_v2(p, d_mods, d_idx, d_nactive, B, d_out, st);
-}
-
 }  // namespace mrinr

@@ -46,6 +46,7 @@ extern "C" void mrinr_free_packed(MrinrPacked* p) {
   cudaFree(p->d_net_wT);
   cudaFree(p->d_net_w16);
   cudaFree(p->d_net_w16p);
+  cudaFree(p->d_net_w16q);
   cudaFree(p->d_layer0);
   cudaFree(p->d_grid);
   cudaFree(p->d_net_bias);
@@ -129,6 +130,7 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     PK_CUDA(cudaMalloc(&p->d_net_wT, (size_t)(L - 1) * H * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_w16, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_w16p, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
+    PK_CUDA(cudaMalloc(&p->d_net_w16q, (size_t)(L - 1) * 2 * (H / 8 + 2) * (H / 2) * 8 * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_layer0, (size_t)3 * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_grid, (size_t)C * 2 * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_bias, (size_t)L * H * sizeof(float)));
@@ -165,6 +167,9 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
                            p->d_net_w16 + (size_t)(l - 1) * H * H, st));
         PK_RC(run_pack_w16_pair(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
                                 p->d_net_w16p + (size_t)(l - 1) * H * H, st));
+        PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], (v->d_net_bias ? v->d_net_bias[l] : nullptr), H,
+                                     precision == MRINR_PREC_BF16,
+                                     p->d_net_w16q + (size_t)(l - 1) * 2 * (H / 8 + 2) * (H / 2) * 8, st));
       }
     }
     PK_CUDA(cudaMemcpyAsync(p->d_last_w, v->d_last_weight, H * sizeof(float), cudaMemcpyDeviceToDevice, st));

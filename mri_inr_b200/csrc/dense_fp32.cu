@@ -63,6 +63,41 @@ __global__ void pack_w16_pair_kernel(const float* __restrict__ w, int H, int use
   out[i] = bits;
 }
 
+// cta_group::2 + bias-in-MMA variant: per (rank r): [kc 0..31][n' 0..127][8] weights as above, followed by one
+// extra K=16 step [kc 32..33][n'][8] whose first two K slots hold the bias split into hi + lo 16-bit parts
+// (b = hi + lo to ~2^-22 relative); the A operand has ones in those two slots, so D = A W^T + b.
+// out is [(2)][34][128][8] = 2 x 69632 bytes per layer.
+__global__ void pack_w16_pair_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias, int H,
+                                          int use_bf16, uint16_t* __restrict__ out) {
+  const int per_rank = (H / 8 + 2) * (H / 2) * 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * per_rank) return;
+  const int r = i / per_rank;
+  const int j = i - r * per_rank;
+  const int e = j & 7;
+  const int np = (j >> 3) % (H / 2);
+  const int kc = (j >> 3) / (H / 2);
+  const int n = r * (H / 2) + np;
+  float v = 0.f;
+  if (kc < H / 8) {
+    v = w[(long long)n * H + kc * 8 + e];
+  } else if (kc == H / 8 && e < 2 && bias != nullptr) {
+    const float b = bias[n];
+    float hi;
+    if (use_bf16) hi = __bfloat162float(__float2bfloat16_rn(b)); else hi = __half2float(__float2half_rn(b));
+    v = (e == 0) ? hi : (b - hi);
+  }
+  uint16_t bits;
+  if (use_bf16) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&b);
+  } else {
+    const __half h = __float2half_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&h);
+  }
+  out[i] = bits;
+}
+
 __device__ __forceinline__ float act_exact(float pre, float w0, int activation) {
   // Sine: modulated_siren.py:54 ; Morlet: :80 (Gaussian on the un-scaled pre-activation)
   const float s = sinf(w0 * pre);
@@ -228,6 +263,13 @@ int run_pack_w16_pair(const float* w, int H, int use_bf16, uint16_t* out, cudaSt
   pack_w16_pair_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(w, H, use_bf16, out);
   count_launch();
   return check_launch("pack_w16_pair");
+}
+
+int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf16, uint16_t* out, cudaStream_t st) {
+  const int n = 2 * (H / 8 + 2) * (H / 2) * 8;
+  pack_w16_pair_bias_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, bias, H, use_bf16, out);
+  count_launch();
+  return check_launch("pack_w16_pair_bias");
 }
 
 int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,

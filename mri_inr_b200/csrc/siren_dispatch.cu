@@ -1,5 +1,5 @@
-// Variant selection for the tensor-core synthesis kernel.  Default: version 3 (CTA pairs, cta_group::2).
-// MRINR_TC_VARIANT=1|2 selects the earlier single-CTA kernels (kept for A/B measurements, see profiles/).
+// Variant selection for the tensor-core synthesis kernel.  Default: version 4 (CTA pairs, two tile slots).
+// MRINR_TC_VARIANT=1|2|3 selects the earlier single-CTA kernels (kept for A/B measurements, see profiles/).
 #include "common.cuh"
 
 #include <cstdlib>
@@ -17,17 +17,22 @@ namespace v3 {
 int launch_siren_tc_v3(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
                        int64_t B, float* d_out, cudaStream_t st);
 }
+namespace v4 {
+int launch_siren_tc_v4(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
+                       int64_t B, float* d_out, cudaStream_t st);
+}
 
 int launch_siren_tc(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
                     int64_t B, float* d_out, cudaStream_t st) {
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("MRINR_TC_VARIANT");
-    variant = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
+    variant = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 4;
   }
   if (variant == 1 || p->L < 3) return v1::launch_siren_tc_v1(p, d_mods, d_idx, d_nactive, B, d_out, st);
   if (variant == 2) return v2::launch_siren_tc_v2(p, d_mods, d_idx, d_nactive, B, d_out, st);
-  return v3::launch_siren_tc_v3(p, d_mods, d_idx, d_nactive, B, d_out, st);
+  if (variant == 3) return v3::launch_siren_tc_v3(p, d_mods, d_idx, d_nactive, B, d_out, st);
+  return v4::launch_siren_tc_v4(p, d_mods, d_idx, d_nactive, B, d_out, st);
 }
 
 }  // namespace mrinr

@@ -1,0 +1,411 @@
+// Fused modulated-SIREN synthesis kernel, version 4: CTA pairs (cta_group::2) + two tiles in flight per CTA.
+//
+// What the profiles of the earlier versions said (profiles/r01_*.md):
+//   v1/v2 (single CTA)      : bound by L2->SM delivery of weights + layer-0 table (670 KB per 128-row tile).
+//   v3 (CTA pairs, chasing) : traffic fixed, but the epilogue warps idle ~21 % of the time waiting for the tail
+//                             of each layer's MMAs, and 7.7 instructions are issued per activation.
+// This version keeps the pair (every CTA stores only its 128 output rows of each layer's weights) and changes
+// the schedule to a ping-pong over two tile slots per CTA:
+//
+//   epilogue warps :  P0(s0) P0(s1) | E1(s0) E1(s1) | E2(s0) E2(s1) | ... | F(s0) P0'(s0) F(s1) P0'(s1) | ...
+//   tensor pipe    :         M1(s0)   M1(s1) M2(s0)   M2(s1) ...        (M_l(s) needs only E_{l-1}(s) complete)
+//
+// While the 8 epilogue warps work on one slot, the MMAs of the other slot run, so neither side waits for the
+// other as long as a phase takes longer than one layer of MMAs (2176 cycles).  One accumulator per slot
+// (2 x 256 TMEM columns).  Every weight slab is used by both slots before it is recycled, so weight traffic per
+// tile halves again (4 tiles share one pass over the weights).
+//
+// Instruction diet for the epilogue (it is the bottleneck: 1 MUFU + ~4 other issue slots per activation):
+//   * the bias is added by the tensor core: a 17th K=16 step multiplies two "ones" columns of A with the bias
+//     split into hi + lo 16-bit halves (exact to 2^-22), so no FADD / bias load in the epilogue;
+//   * layer 0 (2 inputs) is evaluated in place with w0_initial folded into its parameters (sine);
+//   * modulation vectors come from global memory through L1 (warp-uniform 16-byte loads, prefetched one phase ahead).
+//
+// Cross-CTA signalling as in v3: a_full[slot] lives in the leader CTA (one arrival per warp, 16 per phase);
+// w_empty / acc_full come from tcgen05.commit multicast; the peer forwards its w_full to the leader's w_peer.
+// Warp roles per CTA (320 threads): warps 0-7 epilogue; warp 8 lane 0: MMA issuer (leader) / forwarder (peer);
+// warp 9 lane 0: weight producer.
+#include "tc_ptx.cuh"
+
+namespace mrinr {
+namespace v4 {
+
+constexpr int kH = 256;
+constexpr int kTileM = 128;
+constexpr int kSlabBytes = 16384;    // K=64 x N=128 (this CTA's half of the output rows) x 2 B
+constexpr int kBiasSlabBytes = 4096; // K=16 x N=128 x 2 B
+constexpr int kNumSlabs = 5;         // 4 weight slabs + the bias step
+constexpr int kLayerBytes = 4 * kSlabBytes + kBiasSlabBytes;   // per (layer, rank) in the packed array
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = kEpiWarps * 32 + 64;
+constexpr int kMaxLayers = 16;
+constexpr int kTmemCols = 512;
+
+constexpr int kOffA = 0;                                          // [2 slots][64 KB]
+constexpr int kOffOnes = 2 * 65536;                               // [2 kc][128][8] constant "ones" K step
+constexpr int kOffW = kOffOnes + 4096;                            // 4 x 16 KB + 4 KB
+constexpr int kOffL0 = kOffW + kLayerBytes;                       // [3][256] f32
+constexpr int kOffLastW = kOffL0 + 3 * kH * 4;                    // [256] f32
+constexpr int kOffPart = kOffLastW + kH * 4;                      // [2][128] f32
+constexpr int kOffBar = kOffPart + 2 * kTileM * 4;
+constexpr int kOffTmemPtr = kOffBar + 32 * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16;
+
+constexpr int kBarWFull = 0;     // [5] local, transaction based
+constexpr int kBarWPeer = 5;     // [5] leader: the peer's slab has landed
+constexpr int kBarWEmpty = 10;   // [5] both CTAs, via multicast commit
+constexpr int kBarAFull = 15;    // [2] leader: 16 warp arrivals (8 warps x 2 CTAs): operand of slot s complete
+constexpr int kBarAccFull = 17;  // [2] both CTAs, via multicast commit
+
+struct RowInfo {
+  const float* mod_base;   // mods + patch*256 (layer 0); layer l adds l*B*256
+  float* out;              // &out[patch*C + c] or nullptr for a padding row
+};
+
+template <int ACT, bool BF16, bool W0ONE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_tc4_kernel(const SirenTcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int C = P.C, L = P.L;
+  const uint32_t rank = cluster_ctarank();
+
+  float* s_l0 = reinterpret_cast<float*>(smem + kOffL0);
+  float* s_lastw = reinterpret_cast<float*>(smem + kOffLastW);
+  float* s_part = reinterpret_cast<float*>(smem + kOffPart);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
+  const uint32_t sA = smem_u32(smem + kOffA);
+  const uint32_t sOnes = smem_u32(smem + kOffOnes);
+  const uint32_t sW = smem_u32(smem + kOffW);
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto bar = [bar0](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
+
+  const long long n_act = P.nactive ? (long long)*P.nactive : P.B;
+  const long long total_rows = n_act * C;
+  const long long n_tiles = (total_rows + kTileM - 1) / kTileM;
+  const long long n_quads = (n_tiles + 3) / 4;         // a cluster iteration covers 4 tiles: 2 slots x 2 CTAs
+  const long long cluster_id = blockIdx.x >> 1;
+  const long long n_clusters = gridDim.x >> 1;
+  const size_t layer_stride = (size_t)P.B * kH;
+  constexpr bool kFoldW0 = (ACT == MRINR_ACT_SINE);    // layer 0: fold w0_initial into its parameters
+
+  // ---- one-time setup ----
+  for (int i = tid; i < 3 * kH; i += kThreads) s_l0[i] = P.layer0[i] * (kFoldW0 ? P.w0_initial : 1.0f);
+  for (int i = tid; i < kH; i += kThreads) s_lastw[i] = P.last_w[i];
+  for (int i = tid; i < 4096 / 16; i += kThreads) {
+    // ones block: K slots 0 and 1 of every row are 1.0 (they meet the bias hi / lo rows of B), the rest 0
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i < kTileM) v.x = BF16 ? 0x3f803f80u : 0x3c003c00u;
+    reinterpret_cast<uint4*>(smem + kOffOnes)[i] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kNumSlabs; ++s) {
+      mbar_init(bar(kBarWFull + s), 1);
+      mbar_init(bar(kBarWPeer + s), 1);
+      mbar_init(bar(kBarWEmpty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(kBarAFull + s), 2 * kEpiWarps);
+      mbar_init(bar(kBarAccFull + s), 1);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async();         // the ones block is read by the tensor core (async proxy)
+  if (warp == kEpiWarps) tmem_alloc_pair(smem_u32(s_tmem), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp < kEpiWarps) {
+    // =========================== epilogue warps (both CTAs, identical) ===========================
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const int t = q * 32 + lane;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float last_b = P.last_b ? *P.last_b : 0.f;
+
+    RowInfo cur0{nullptr, nullptr}, cur1{nullptr, nullptr};      // rows of the tiles in slot 0 / 1
+    RowInfo prev0{nullptr, nullptr}, prev1{nullptr, nullptr};    // rows of the previous iteration's tiles
+    bool have_prev = false;
+    uint32_t it = 0;                                   // cluster iteration (quad) counter
+
+    auto publish = [&](int slot) {                     // this warp's part of A[slot] is written and fenced
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar(kBarAFull + slot), 0);
+    };
+    auto store_chunk = [&](int slot, int j, const uint32_t (&pk)[16]) {
+      const int kc0 = (half * 4 + j) * 4;
+      uint8_t* base = smem + kOffA + slot * 65536 + t * 16;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+        *reinterpret_cast<uint4*>(base + (kc0 + qq) * 2048) =
+            make_uint4(pk[qq * 4 + 0], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
+    };
+
+    // output phase of a finished tile: y = sin(w0 (h_{L-1} . w_last + b_last)), h_{L-1} = act(D) * mod
+    auto final_phase = [&](int slot, const RowInfo& ri, uint32_t ev) {
+      mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 5);
+      tc_fence_after();
+      const uint32_t acc_col = (uint32_t)slot * 256u + (uint32_t)half * 128u;
+      const float* mod_l = ri.mod_base + (size_t)(L - 1) * layer_stride + half * 128;
+      const float* lw = s_lastw + half * 128;
+      float dot = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v[32];
+        tmem_ld32(taddr_row + acc_col + j * 32, v);
+        float4 m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = __ldg(reinterpret_cast<const float4*>(mod_l + j * 32) + i);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(lw + j * 32 + i * 4);
+          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 0]), P.w0) * m[i].x, w.x, dot);
+          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 1]), P.w0) * m[i].y, w.y, dot);
+          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 2]), P.w0) * m[i].z, w.z, dot);
+          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 3]), P.w0) * m[i].w, w.w, dot);
+        }
+      }
+      tc_fence_before();
+      float* part = s_part + slot * kTileM;
+      if (half == 1) {
+        part[t] = dot;
+        asm volatile("bar.arrive %0, 64;" ::"r"(2 + q) : "memory");
+      } else {
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        // output layer: always sine, never modulated (modulated_siren.py:211-213, :233)
+        if (ri.out != nullptr) *ri.out = sinf(P.w0 * (dot + part[t] + last_b));
+      }
+    };
+
+    for (long long quad = cluster_id; quad < n_quads; quad += n_clusters, ++it) {
+      const uint32_t ev0 = it * (uint32_t)(L - 1);     // event counter of this iteration's layer 1 (per slot)
+      // ---- per slot: finish the previous tile of the slot, then produce the layer-0 operand of the new one ----
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        if (have_prev) final_phase(slot, slot ? prev1 : prev0, ev0 - 1u);
+        const long long tile = quad * 4 + slot * 2 + rank;     // may be a phantom tile (>= n_tiles)
+        const long long R0 = tile * kTileM;
+        const long long pc0 = R0 / C;
+        const int c0 = (int)(R0 - pc0 * C);
+        RowInfo my{nullptr, nullptr};
+        float g0, g1;
+        {
+          long long pc = pc0 + (t >= C - c0 ? 1 : 0);
+          if (pc >= n_act) pc = n_act - 1;
+          const long long patch = P.idx ? (long long)P.idx[pc] : pc;
+          my.mod_base = P.mods + (size_t)patch * kH;
+          int c = c0 + t;
+          if (c >= C) c -= C;
+          if (R0 + t < total_rows) my.out = P.out + patch * C + c;
+          const float2 g = __ldg(reinterpret_cast<const float2*>(P.grid) + c);
+          g0 = g.x;
+          g1 = g.y;
+        }
+        if (slot) cur1 = my; else cur0 = my;
+        // layer 0 (modulated_siren.py:154-156 with dim_in = 2): h = act(w0_initial (W0 g + b0)) * mod_0
+        const float* mod_l = my.mod_base + half * 128;
+        prefetch_l1(mod_l + layer_stride + (lane & 3) * 32);
+        const float* wa = s_l0 + half * 128;
+        const float* wb = s_l0 + kH + half * 128;
+        const float* wc = s_l0 + 2 * kH + half * 128;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          float4 m[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = __ldg(reinterpret_cast<const float4*>(mod_l + j * 32) + i);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(wa + j * 32 + i * 4);
+            const float4 b = *reinterpret_cast<const float4*>(wb + j * 32 + i * 4);
+            const float4 cc = *reinterpret_cast<const float4*>(wc + j * 32 + i * 4);
+            float h[4];
+            const float p0 = fmaf(g1, b.x, fmaf(g0, a.x, cc.x)), p1 = fmaf(g1, b.y, fmaf(g0, a.y, cc.y));
+            const float p2 = fmaf(g1, b.z, fmaf(g0, a.z, cc.z)), p3 = fmaf(g1, b.w, fmaf(g0, a.w, cc.w));
+            if (kFoldW0) {
+              h[0] = __sinf(p0); h[1] = __sinf(p1); h[2] = __sinf(p2); h[3] = __sinf(p3);
+            } else {
+              h[0] = act_fast<ACT, false>(p0, P.w0_initial); h[1] = act_fast<ACT, false>(p1, P.w0_initial);
+              h[2] = act_fast<ACT, false>(p2, P.w0_initial); h[3] = act_fast<ACT, false>(p3, P.w0_initial);
+            }
+            pk[i * 2 + 0] = pack2<BF16>(h[0] * m[i].x, h[1] * m[i].y);
+            pk[i * 2 + 1] = pack2<BF16>(h[2] * m[i].z, h[3] * m[i].w);
+          }
+          store_chunk(slot, j, pk);
+        }
+        publish(slot);
+      }
+
+      // ---- hidden layers 1 .. L-2, alternating slots: the other slot's MMAs run underneath ----
+      for (int l = 1; l <= L - 2; ++l) {
+        const uint32_t ev = ev0 + (uint32_t)(l - 1);
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          const uint32_t acc_col = (uint32_t)slot * 256u + (uint32_t)half * 128u;
+          const float* mod_l = (slot ? cur1 : cur0).mod_base + (size_t)l * layer_stride + half * 128;
+          prefetch_l1(mod_l + layer_stride + (lane & 3) * 32);
+          mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 4);
+          tc_fence_after();
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            uint32_t v[32];
+            tmem_ld32(taddr_row + acc_col + j * 32, v);
+            float4 m[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = __ldg(reinterpret_cast<const float4*>(mod_l + j * 32) + i);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float h0 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 0]), P.w0) * m[i].x;
+              const float h1 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 1]), P.w0) * m[i].y;
+              const float h2 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 2]), P.w0) * m[i].z;
+              const float h3 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 3]), P.w0) * m[i].w;
+              pk[i * 2 + 0] = pack2<BF16>(h0, h1);
+              pk[i * 2 + 1] = pack2<BF16>(h2, h3);
+            }
+            store_chunk(slot, j, pk);
+          }
+          tc_fence_before();
+          publish(slot);
+        }
+      }
+      prev0 = cur0;
+      prev1 = cur1;
+      have_prev = true;
+    }
+    if (have_prev) {
+      const uint32_t ev_last = it * (uint32_t)(L - 1) - 1u;
+      final_phase(0, prev0, ev_last);
+      final_phase(1, prev1, ev_last);
+    }
+  } else if (warp == kEpiWarps) {
+    if (lane == 0 && rank == 0) {
+      // =========================== MMA issuer (leader CTA) ===========================
+      const uint32_t idesc = make_idesc(BF16 ? 1 : 0, 2 * kTileM, kH);
+      const uint64_t ones_desc = make_smem_desc(sOnes, 2048, 128);
+      uint32_t ev = 0;
+      for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+        for (int l = 1; l < L; ++l, ++ev) {
+#pragma unroll 1
+          for (int slot = 0; slot < 2; ++slot) {
+            const uint64_t adesc0 = make_smem_desc(sA + slot * 65536, 2048, 128);
+            const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+            mbar_wait_cluster(bar(kBarAFull + slot), ev & 1u, P.errflag, 1);
+#pragma unroll 1
+            for (int s = 0; s < kNumSlabs; ++s) {
+              if (slot == 0) {
+                mbar_wait(bar(kBarWFull + s), ev & 1u, P.errflag, 2);
+                mbar_wait_cluster(bar(kBarWPeer + s), ev & 1u, P.errflag, 8);
+              }
+              tc_fence_after();
+              const uint64_t bdesc0 = make_smem_desc(sW + s * kSlabBytes, 2048, 128);
+              if (s < 4) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t ad = adesc0 + (uint64_t)(((s * 4 + kk) * 4096) >> 4);
+                  const uint64_t bd = bdesc0 + (uint64_t)((kk * 4096) >> 4);
+                  umma_f16_pair(d_tmem, ad, bd, idesc, (s | kk) != 0 ? 1u : 0u);
+                }
+              } else {
+                umma_f16_pair(d_tmem, ones_desc, bdesc0, idesc, 1u);       // + bias
+              }
+              if (slot == 1) umma_commit_pair(bar(kBarWEmpty + s), 3);      // both slots have used this slab
+            }
+            umma_commit_pair(bar(kBarAccFull + slot), 3);
+          }
+        }
+      }
+    } else if (lane == 0) {
+      // =========================== forwarder (peer CTA): my slab has landed ===========================
+      uint32_t ev = 0;
+      for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+        for (int l = 1; l < L; ++l, ++ev) {
+#pragma unroll 1
+          for (int s = 0; s < kNumSlabs; ++s) {
+            mbar_wait(bar(kBarWFull + s), ev & 1u, P.errflag, 9);
+            mbar_arrive_cluster(bar(kBarWPeer + s), 0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== weight producer (both CTAs: own half of every slab) ===========================
+    if (lane == 0) {
+      uint32_t ev = 0;
+      for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+        for (int l = 1; l < L; ++l, ++ev) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(P.w16q) + ((size_t)(l - 1) * 2 + rank) * kLayerBytes;
+#pragma unroll 1
+          for (int s = 0; s < kNumSlabs; ++s) {
+            const uint32_t bytes = s < 4 ? kSlabBytes : kBiasSlabBytes;
+            mbar_wait(bar(kBarWEmpty + s), (ev & 1u) ^ 1u, P.errflag, 7);
+            mbar_expect_tx(bar(kBarWFull + s), bytes);
+            bulk_g2s(sW + s * kSlabBytes, src + (size_t)s * kSlabBytes, bytes, bar(kBarWFull + s));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- teardown: both CTAs must be done before the pair's TMEM is released ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == kEpiWarps) tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
+template <int ACT, bool BF16, bool W0ONE>
+static int launch_one(const SirenTcParams& P, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    MRINR_CUDA(cudaFuncSetAttribute(siren_tc4_kernel<ACT, BF16, W0ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBytes));
+    configured = true;
+  }
+  siren_tc4_kernel<ACT, BF16, W0ONE><<<grid, kThreads, kSmemBytes, st>>>(P);
+  count_launch();
+  return check_launch("siren_tc4");
+}
+
+int launch_siren_tc_v4(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
+                       int64_t B, float* d_out, cudaStream_t st) {
+  MRINR_REQUIRE(p->H == kH && p->L <= kMaxLayers && p->L >= 3 && p->C >= kTileM, MRINR_E_UNSUPPORTED,
+                "siren_tc4: unsupported configuration (H=%d L=%d C=%d)", p->H, p->L, p->C);
+  SirenTcParams P;
+  P.table0 = p->d_table0; P.w16 = p->d_net_w16; P.w16p = p->d_net_w16p; P.w16q = p->d_net_w16q;
+  P.layer0 = p->d_layer0; P.grid = p->d_grid; P.w0_initial = p->w0_initial;
+  P.bias = p->d_net_bias; P.last_w = p->d_last_w;
+  P.last_b = p->d_last_b; P.mods = d_mods; P.idx = d_idx; P.nactive = d_nactive; P.out = d_out;
+  P.errflag = p->d_errflag; P.B = B; P.C = p->C; P.L = p->L; P.w0 = p->w0;
+  const long long n_tiles = (B * p->C + kTileM - 1) / kTileM;
+  const long long n_quads = (n_tiles + 3) / 4;
+  long long clusters = p->num_sms / 2;
+  if (clusters > n_quads) clusters = n_quads;
+  const int grid = (int)(clusters * 2);
+  const bool w0one = (p->w0 == 1.0f);
+  const bool bf16 = (p->precision == MRINR_PREC_BF16);
+  const bool morlet = (p->activation == MRINR_ACT_MORLET);
+#define MRINR_TC_CASE(A, Bf, W) return launch_one<A, Bf, W>(P, grid, st)
+  if (!morlet) {
+    if (!bf16) { if (w0one) MRINR_TC_CASE(MRINR_ACT_SINE, false, true); else MRINR_TC_CASE(MRINR_ACT_SINE, false, false); }
+    else       { if (w0one) MRINR_TC_CASE(MRINR_ACT_SINE, true, true);  else MRINR_TC_CASE(MRINR_ACT_SINE, true, false); }
+  } else {
+    if (!bf16) { if (w0one) MRINR_TC_CASE(MRINR_ACT_MORLET, false, true); else MRINR_TC_CASE(MRINR_ACT_MORLET, false, false); }
+    else       { if (w0one) MRINR_TC_CASE(MRINR_ACT_MORLET, true, true);  else MRINR_TC_CASE(MRINR_ACT_MORLET, true, false); }
+  }
+#undef MRINR_TC_CASE
+}
+
+}  // namespace v4
+}  // namespace mrinr

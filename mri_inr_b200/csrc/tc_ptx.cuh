@@ -199,6 +199,7 @@ struct SirenTcParams {
   const float* table0;      // [C,256]
   const uint16_t* w16;      // [(L-1)][32][256][8]
   const uint16_t* w16p;     // [(L-1)][2][32][128][8]   (cta_group::2 path)
+  const uint16_t* w16q;     // [(L-1)][2][34][128][8]   (cta_group::2 path, bias carried by a 17th K step)
   const float* layer0;      // [3][256]  W_0[:,0], W_0[:,1], b_0
   const float* grid;        // [C][2]
   float w0_initial;

@@ -57,6 +57,26 @@ constexpr int kBarWEmpty = 10;   // [5] both CTAs, via multicast commit
 constexpr int kBarAFull = 15;    // [2] leader: 16 warp arrivals (8 warps x 2 CTAs): operand of slot s complete
 constexpr int kBarAccFull = 17;  // [2] both CTAs, via multicast commit
 
+#ifdef MRINR_TIMELINE
+// development aid: per-phase timestamps of one warp (see tools/timeline.py); compiled out by default
+__device__ long long g_timeline[8192];
+__device__ int g_timeline_n;
+#define TL(tag)                                                                          \
+  do {                                                                                   \
+    if (lane == 0 && (warp == 0 || warp == 5 || warp == 8) && blockIdx.x < 2) {           \
+      const int _i = atomicAdd(&g_timeline_n, 1);                                        \
+      if (_i < 2048) {                                                                   \
+        g_timeline[_i * 4 + 0] = (long long)blockIdx.x * 100 + warp;                     \
+        g_timeline[_i * 4 + 1] = (tag);                                                  \
+        g_timeline[_i * 4 + 2] = clock64();                                              \
+        g_timeline[_i * 4 + 3] = 0;                                                      \
+      }                                                                                  \
+    }                                                                                    \
+  } while (0)
+#else
+#define TL(tag) do { } while (0)
+#endif
+
 struct RowInfo {
   const float* mod_base;   // mods + patch*256 (layer 0); layer l adds l*B*256
   float* out;              // &out[patch*C + c] or nullptr for a padding row
@@ -149,7 +169,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 
     // output phase of a finished tile: y = sin(w0 (h_{L-1} . w_last + b_last)), h_{L-1} = act(D) * mod
     auto final_phase = [&](int slot, const RowInfo& ri, uint32_t ev) {
+      TL(1000 + slot);
       mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 5);
+      TL(1010 + slot);
       tc_fence_after();
       const uint32_t acc_col = (uint32_t)slot * 256u + (uint32_t)half * 128u;
       const float* mod_l = ri.mod_base + (size_t)(L - 1) * layer_stride + half * 128;
@@ -209,6 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           g1 = g.y;
         }
         if (slot) cur1 = my; else cur0 = my;
+        TL(2000 + slot);
         // layer 0 (modulated_siren.py:154-156 with dim_in = 2): h = act(w0_initial (W0 g + b0)) * mod_0
         const float* mod_l = my.mod_base + half * 128;
         prefetch_l1(mod_l + layer_stride + (lane & 3) * 32);
@@ -241,6 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           store_chunk(slot, j, pk);
         }
         publish(slot);
+        TL(2010 + slot);
       }
 
       // ---- hidden layers 1 .. L-2, alternating slots: the other slot's MMAs run underneath ----
@@ -251,7 +275,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           const uint32_t acc_col = (uint32_t)slot * 256u + (uint32_t)half * 128u;
           const float* mod_l = (slot ? cur1 : cur0).mod_base + (size_t)l * layer_stride + half * 128;
           prefetch_l1(mod_l + layer_stride + (lane & 3) * 32);
+          TL(3000 + l * 10 + slot);
           mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 4);
+          TL(4000 + l * 10 + slot);
           tc_fence_after();
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
@@ -275,6 +301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           }
           tc_fence_before();
           publish(slot);
+          TL(5000 + l * 10 + slot);
         }
       }
       prev0 = cur0;
@@ -287,39 +314,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       final_phase(1, prev1, ev_last);
     }
   } else if (warp == kEpiWarps) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // =========================== MMA issuer (leader CTA) ===========================
+      // The whole warp runs the loop converged; one elected lane issues the tcgen05 instructions, so that all
+      // descriptor arithmetic stays warp-uniform (uniform registers, no per-instruction waterfall).
       const uint32_t idesc = make_idesc(BF16 ? 1 : 0, 2 * kTileM, kH);
-      const uint64_t ones_desc = make_smem_desc(sOnes, 2048, 128);
+      const uint32_t desc_hi = smem_desc_hi(128);
+      const uint32_t a_lo0 = smem_desc_lo(sA, 2048);
+      const uint32_t ones_lo = smem_desc_lo(sOnes, 2048);
+      const uint32_t b_lo0 = smem_desc_lo(sW, 2048);
       uint32_t ev = 0;
       for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
         for (int l = 1; l < L; ++l, ++ev) {
-#pragma unroll 1
+#pragma unroll
           for (int slot = 0; slot < 2; ++slot) {
-            const uint64_t adesc0 = make_smem_desc(sA + slot * 65536, 2048, 128);
+            const uint32_t a_lo = a_lo0 + (uint32_t)slot * (65536u >> 4);
             const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-            mbar_wait_cluster(bar(kBarAFull + slot), ev & 1u, P.errflag, 1);
-#pragma unroll 1
+            TL(6000 + l * 10 + slot);
+            mbar_wait_backoff(bar(kBarAFull + slot), ev & 1u, P.errflag, 1, 32);
+            TL(7000 + l * 10 + slot);
+#pragma unroll
             for (int s = 0; s < kNumSlabs; ++s) {
               if (slot == 0) {
-                mbar_wait(bar(kBarWFull + s), ev & 1u, P.errflag, 2);
-                mbar_wait_cluster(bar(kBarWPeer + s), ev & 1u, P.errflag, 8);
+                mbar_wait_backoff(bar(kBarWFull + s), ev & 1u, P.errflag, 2, 32);
+                mbar_wait_backoff(bar(kBarWPeer + s), ev & 1u, P.errflag, 8, 32);
               }
               tc_fence_after();
-              const uint64_t bdesc0 = make_smem_desc(sW + s * kSlabBytes, 2048, 128);
-              if (s < 4) {
+              if (elect_one()) {
+                const uint32_t b_lo = b_lo0 + (uint32_t)s * (kSlabBytes >> 4);
+                if (s < 4) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint64_t ad = adesc0 + (uint64_t)(((s * 4 + kk) * 4096) >> 4);
-                  const uint64_t bd = bdesc0 + (uint64_t)((kk * 4096) >> 4);
-                  umma_f16_pair(d_tmem, ad, bd, idesc, (s | kk) != 0 ? 1u : 0u);
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_f16_pair_lohi(d_tmem, a_lo + (uint32_t)(s * 4 + kk) * 256u, b_lo + (uint32_t)kk * 256u, desc_hi,
+                                       idesc, (s | kk) != 0 ? 1u : 0u);
+                } else {
+                  umma_f16_pair_lohi(d_tmem, ones_lo, b_lo, desc_hi, idesc, 1u);      // + bias
                 }
-              } else {
-                umma_f16_pair(d_tmem, ones_desc, bdesc0, idesc, 1u);       // + bias
+                if (slot == 1 && s == kNumSlabs - 1) {
+                  // both slots have consumed this layer's slabs: hand all of them back with one commit each
+#pragma unroll
+                  for (int r = 0; r < kNumSlabs; ++r) umma_commit_pair(bar(kBarWEmpty + r), 3);
+                }
               }
-              if (slot == 1) umma_commit_pair(bar(kBarWEmpty + s), 3);      // both slots have used this slab
+              __syncwarp();
             }
-            umma_commit_pair(bar(kBarAccFull + slot), 3);
+            if (elect_one()) umma_commit_pair(bar(kBarAccFull + slot), 3);
+            __syncwarp();
+            TL(8000 + l * 10 + slot);
           }
         }
       }
@@ -330,7 +371,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         for (int l = 1; l < L; ++l, ++ev) {
 #pragma unroll 1
           for (int s = 0; s < kNumSlabs; ++s) {
-            mbar_wait(bar(kBarWFull + s), ev & 1u, P.errflag, 9);
+            mbar_wait_backoff(bar(kBarWFull + s), ev & 1u, P.errflag, 9);
             mbar_arrive_cluster(bar(kBarWPeer + s), 0);
           }
         }
@@ -347,7 +388,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 #pragma unroll 1
           for (int s = 0; s < kNumSlabs; ++s) {
             const uint32_t bytes = s < 4 ? kSlabBytes : kBiasSlabBytes;
-            mbar_wait(bar(kBarWEmpty + s), (ev & 1u) ^ 1u, P.errflag, 7);
+            mbar_wait_backoff(bar(kBarWEmpty + s), (ev & 1u) ^ 1u, P.errflag, 7);
             mbar_expect_tx(bar(kBarWFull + s), bytes);
             bulk_g2s(sW + s * kSlabBytes, src + (size_t)s * kSlabBytes, bytes, bar(kBarWFull + s));
           }
@@ -409,3 +450,16 @@ int launch_siren_tc_v4(const MrinrPacked* p, const float* d_mods, const int32_t*
 
 }  // namespace v4
 }  // namespace mrinr
+
+#ifdef MRINR_TIMELINE
+extern "C" __attribute__((visibility("default"))) int mrinr_debug_timeline(long long* host_out, int max_entries) {
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, mrinr::v4::g_timeline_n, sizeof(int));
+  if (n > max_entries) n = max_entries;
+  if (n > 2048) n = 2048;
+  cudaMemcpyFromSymbol(host_out, mrinr::v4::g_timeline, (size_t)n * 4 * sizeof(long long));
+  int zero = 0;
+  cudaMemcpyToSymbol(mrinr::v4::g_timeline_n, &zero, sizeof(int));
+  return n;
+}
+#endif

@@ -40,6 +40,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t
     if (clock64() - t0 > kWatchdogCycles) mbar_timeout(errflag, code);
   }
 }
+// wait used by the single-thread roles (MMA issuer, producer, forwarder): backs off with nanosleep between probes so
+// that the spinning warp does not take issue slots from the two epilogue warps of its SM sub-partition
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int32_t* errflag, int code,
+                                                  unsigned ns = 64) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > kWatchdogCycles) mbar_timeout(errflag, code);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -191,6 +202,37 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, u
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// One lane of a converged warp (elect.sync): the tcgen05 issue pattern that lets the compiler keep descriptors in
+// uniform registers.  Issuing from a divergent `if (lane == 0)` region instead makes ptxas wrap every UTCHMMA in an
+// ELECT / R2UR waterfall loop (~25 instructions, ~200 cycles per MMA: measured, profiles/r01_siren_v4a.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(p));
+  return p != 0;
+}
+// descriptor = {lo, hi}: only the low word (start address, LBO) changes between K steps
+__device__ __forceinline__ void umma_f16_pair_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14);   // version 1, no swizzle, base offset 0
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

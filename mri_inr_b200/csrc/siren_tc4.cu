@@ -158,41 +158,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(bar(kBarAFull + slot), 0);
     };
-    auto store_chunk = [&](int slot, int j, const uint32_t (&pk)[16]) {
-      const int kc0 = (half * 4 + j) * 4;
-      uint8_t* base = smem + kOffA + slot * 65536 + t * 16;
+    // 16 activations x = pre-activation (bias included) -> h = act(x) * mod, packed to 8 x (2 x 16 bit).
+    // Sine with w0 == 1 uses the order-pinned pipeline (sines of group g, then multiply + pack of group g-1).
+    auto act16_pack = [&](const float (&x)[16], const float4 (&m)[4], uint32_t (&pk)[8], float w0) {
+      if (ACT == MRINR_ACT_SINE) {
+        float s[16];
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq)
-        *reinterpret_cast<uint4*>(base + (kc0 + qq) * 2048) =
-            make_uint4(pk[qq * 4 + 0], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s[g * 4 + i] = vsin(W0ONE ? x[g * 4 + i] : w0 * x[g * 4 + i]);
+          if (g > 0) {
+            const float4 mm = m[g - 1];
+            pk[(g - 1) * 2 + 0] = vpack2<BF16>(vmul(s[g * 4 - 4], mm.x), vmul(s[g * 4 - 3], mm.y));
+            pk[(g - 1) * 2 + 1] = vpack2<BF16>(vmul(s[g * 4 - 2], mm.z), vmul(s[g * 4 - 1], mm.w));
+          }
+        }
+        pk[6] = vpack2<BF16>(vmul(s[12], m[3].x), vmul(s[13], m[3].y));
+        pk[7] = vpack2<BF16>(vmul(s[14], m[3].z), vmul(s[15], m[3].w));
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          pk[g * 2 + 0] = pack2<BF16>(act_fast<ACT, W0ONE>(x[g * 4 + 0], w0) * m[g].x,
+                                      act_fast<ACT, W0ONE>(x[g * 4 + 1], w0) * m[g].y);
+          pk[g * 2 + 1] = pack2<BF16>(act_fast<ACT, W0ONE>(x[g * 4 + 2], w0) * m[g].z,
+                                      act_fast<ACT, W0ONE>(x[g * 4 + 3], w0) * m[g].w);
+        }
+      }
+    };
+    auto store16 = [&](int slot, int hc, const uint32_t (&pk)[8]) {   // columns half*128 + hc*16 .. +15 of row t
+      uint8_t* base = smem + kOffA + slot * 65536 + (half * 16 + hc * 2) * 2048 + t * 16;
+      *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(base + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
+    auto load_mods16 = [&](const float* mod_l, int hc, float4 (&m)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = __ldg(reinterpret_cast<const float4*>(mod_l + hc * 16) + i);
+    };
+    auto as_float16 = [&](const uint32_t (&v)[16], float (&x)[16]) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
     };
 
     // output phase of a finished tile: y = sin(w0 (h_{L-1} . w_last + b_last)), h_{L-1} = act(D) * mod
     auto final_phase = [&](int slot, const RowInfo& ri, uint32_t ev) {
+      const float* mod_l = ri.mod_base + (size_t)(L - 1) * layer_stride + half * 128;
+      const float* lw = s_lastw + half * 128;
+      const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)half * 128u;
+      float4 ma[4], mb[4];
+      load_mods16(mod_l, 0, ma);
       TL(1000 + slot);
       mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 5);
       TL(1010 + slot);
       tc_fence_after();
-      const uint32_t acc_col = (uint32_t)slot * 256u + (uint32_t)half * 128u;
-      const float* mod_l = ri.mod_base + (size_t)(L - 1) * layer_stride + half * 128;
-      const float* lw = s_lastw + half * 128;
+      uint32_t va[16], vb[16];
+      tmem_ld16(tcol, va);
       float dot = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        uint32_t v[32];
-        tmem_ld32(taddr_row + acc_col + j * 32, v);
-        float4 m[8];
+      auto dot16 = [&](const uint32_t (&v)[16], const float4 (&m)[4], int hc) {
+        float x[16];
+        as_float16(v, x);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = __ldg(reinterpret_cast<const float4*>(mod_l + j * 32) + i);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 w = *reinterpret_cast<const float4*>(lw + j * 32 + i * 4);
-          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 0]), P.w0) * m[i].x, w.x, dot);
-          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 1]), P.w0) * m[i].y, w.y, dot);
-          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 2]), P.w0) * m[i].z, w.z, dot);
-          dot = fmaf(act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 3]), P.w0) * m[i].w, w.w, dot);
+        for (int g = 0; g < 4; ++g) {
+          const float4 w = *reinterpret_cast<const float4*>(lw + hc * 16 + g * 4);
+          float h0, h1, h2, h3;
+          if (ACT == MRINR_ACT_SINE) {
+            h0 = vsin(W0ONE ? x[g * 4 + 0] : P.w0 * x[g * 4 + 0]); h1 = vsin(W0ONE ? x[g * 4 + 1] : P.w0 * x[g * 4 + 1]);
+            h2 = vsin(W0ONE ? x[g * 4 + 2] : P.w0 * x[g * 4 + 2]); h3 = vsin(W0ONE ? x[g * 4 + 3] : P.w0 * x[g * 4 + 3]);
+          } else {
+            h0 = act_fast<ACT, W0ONE>(x[g * 4 + 0], P.w0); h1 = act_fast<ACT, W0ONE>(x[g * 4 + 1], P.w0);
+            h2 = act_fast<ACT, W0ONE>(x[g * 4 + 2], P.w0); h3 = act_fast<ACT, W0ONE>(x[g * 4 + 3], P.w0);
+          }
+          dot = fmaf(h0 * m[g].x, w.x, dot);
+          dot = fmaf(h1 * m[g].y, w.y, dot);
+          dot = fmaf(h2 * m[g].z, w.z, dot);
+          dot = fmaf(h3 * m[g].w, w.w, dot);
         }
+      };
+#pragma unroll 1
+      for (int hp = 0; hp < 4; ++hp) {
+        tmem_ld_wait();
+        tmem_ld16(tcol + (uint32_t)(hp * 2 + 1) * 16u, vb);
+        load_mods16(mod_l, hp * 2 + 1, mb);
+        dot16(va, ma, hp * 2);
+        tmem_ld_wait();
+        if (hp < 3) {
+          tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
+          load_mods16(mod_l, hp * 2 + 2, ma);
+        }
+        dot16(vb, mb, hp * 2 + 1);
       }
       tc_fence_before();
       float* part = s_part + slot * kTileM;
@@ -206,6 +258,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       }
     };
 
+    // first tile of this CTA and the (constant) step to the next one, without 64-bit divisions in the loop
+    const long long rows_step = n_clusters * 4 * (long long)kTileM;
+    const long long step_pc = rows_step / C;
+    const int step_c = (int)(rows_step - step_pc * C);
+    long long pc0s[2];
+    int c0s[2];
+    for (int slot = 0; slot < 2; ++slot) {
+      const long long R0 = (cluster_id * 4 + slot * 2 + rank) * (long long)kTileM;
+      pc0s[slot] = R0 / C;
+      c0s[slot] = (int)(R0 - pc0s[slot] * C);
+    }
+    long long pc0_0 = pc0s[0], pc0_1 = pc0s[1];
+    int c0_0 = c0s[0], c0_1 = c0s[1];
+
     for (long long quad = cluster_id; quad < n_quads; quad += n_clusters, ++it) {
       const uint32_t ev0 = it * (uint32_t)(L - 1);     // event counter of this iteration's layer 1 (per slot)
       // ---- per slot: finish the previous tile of the slot, then produce the layer-0 operand of the new one ----
@@ -214,8 +280,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         if (have_prev) final_phase(slot, slot ? prev1 : prev0, ev0 - 1u);
         const long long tile = quad * 4 + slot * 2 + rank;     // may be a phantom tile (>= n_tiles)
         const long long R0 = tile * kTileM;
-        const long long pc0 = R0 / C;
-        const int c0 = (int)(R0 - pc0 * C);
+        const long long pc0 = slot ? pc0_1 : pc0_0;
+        const int c0 = slot ? c0_1 : c0_0;
         RowInfo my{nullptr, nullptr};
         float g0, g1;
         {
@@ -238,66 +304,95 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         const float* wa = s_l0 + half * 128;
         const float* wb = s_l0 + kH + half * 128;
         const float* wc = s_l0 + 2 * kH + half * 128;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          float4 m[8];
+        float4 ma[4], mb[4];
+        load_mods16(mod_l, 0, ma);
+        auto layer0_16 = [&](int hc, const float4 (&m)[4]) {
+          float x[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) m[i] = __ldg(reinterpret_cast<const float4*>(mod_l + j * 32) + i);
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 a = *reinterpret_cast<const float4*>(wa + j * 32 + i * 4);
-            const float4 b = *reinterpret_cast<const float4*>(wb + j * 32 + i * 4);
-            const float4 cc = *reinterpret_cast<const float4*>(wc + j * 32 + i * 4);
-            float h[4];
-            const float p0 = fmaf(g1, b.x, fmaf(g0, a.x, cc.x)), p1 = fmaf(g1, b.y, fmaf(g0, a.y, cc.y));
-            const float p2 = fmaf(g1, b.z, fmaf(g0, a.z, cc.z)), p3 = fmaf(g1, b.w, fmaf(g0, a.w, cc.w));
-            if (kFoldW0) {
-              h[0] = __sinf(p0); h[1] = __sinf(p1); h[2] = __sinf(p2); h[3] = __sinf(p3);
-            } else {
-              h[0] = act_fast<ACT, false>(p0, P.w0_initial); h[1] = act_fast<ACT, false>(p1, P.w0_initial);
-              h[2] = act_fast<ACT, false>(p2, P.w0_initial); h[3] = act_fast<ACT, false>(p3, P.w0_initial);
-            }
-            pk[i * 2 + 0] = pack2<BF16>(h[0] * m[i].x, h[1] * m[i].y);
-            pk[i * 2 + 1] = pack2<BF16>(h[2] * m[i].z, h[3] * m[i].w);
+          for (int g = 0; g < 4; ++g) {
+            const float4 a = *reinterpret_cast<const float4*>(wa + hc * 16 + g * 4);
+            const float4 b = *reinterpret_cast<const float4*>(wb + hc * 16 + g * 4);
+            const float4 cc = *reinterpret_cast<const float4*>(wc + hc * 16 + g * 4);
+            x[g * 4 + 0] = fmaf(g1, b.x, fmaf(g0, a.x, cc.x));
+            x[g * 4 + 1] = fmaf(g1, b.y, fmaf(g0, a.y, cc.y));
+            x[g * 4 + 2] = fmaf(g1, b.z, fmaf(g0, a.z, cc.z));
+            x[g * 4 + 3] = fmaf(g1, b.w, fmaf(g0, a.w, cc.w));
           }
-          store_chunk(slot, j, pk);
+          uint32_t pk[8];
+          if (kFoldW0) {
+            // w0_initial is folded into the parameters: x is already the sine's argument
+            float s[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) s[g * 4 + i] = vsin(x[g * 4 + i]);
+              if (g > 0) {
+                const float4 mm = m[g - 1];
+                pk[(g - 1) * 2 + 0] = vpack2<BF16>(vmul(s[g * 4 - 4], mm.x), vmul(s[g * 4 - 3], mm.y));
+                pk[(g - 1) * 2 + 1] = vpack2<BF16>(vmul(s[g * 4 - 2], mm.z), vmul(s[g * 4 - 1], mm.w));
+              }
+            }
+            pk[6] = vpack2<BF16>(vmul(s[12], m[3].x), vmul(s[13], m[3].y));
+            pk[7] = vpack2<BF16>(vmul(s[14], m[3].z), vmul(s[15], m[3].w));
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              pk[g * 2 + 0] = pack2<BF16>(act_fast<ACT, false>(x[g * 4 + 0], P.w0_initial) * m[g].x,
+                                          act_fast<ACT, false>(x[g * 4 + 1], P.w0_initial) * m[g].y);
+              pk[g * 2 + 1] = pack2<BF16>(act_fast<ACT, false>(x[g * 4 + 2], P.w0_initial) * m[g].z,
+                                          act_fast<ACT, false>(x[g * 4 + 3], P.w0_initial) * m[g].w);
+            }
+          }
+          store16(slot, hc, pk);
+        };
+#pragma unroll 1
+        for (int hp = 0; hp < 4; ++hp) {
+          load_mods16(mod_l, hp * 2 + 1, mb);
+          layer0_16(hp * 2, ma);
+          if (hp < 3) load_mods16(mod_l, hp * 2 + 2, ma);
+          layer0_16(hp * 2 + 1, mb);
         }
         publish(slot);
         TL(2010 + slot);
       }
+      // advance both slots to the next quad of this cluster
+      pc0_0 += step_pc; c0_0 += step_c; if (c0_0 >= C) { c0_0 -= C; ++pc0_0; }
+      pc0_1 += step_pc; c0_1 += step_c; if (c0_1 >= C) { c0_1 -= C; ++pc0_1; }
 
       // ---- hidden layers 1 .. L-2, alternating slots: the other slot's MMAs run underneath ----
       for (int l = 1; l <= L - 2; ++l) {
         const uint32_t ev = ev0 + (uint32_t)(l - 1);
 #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
-          const uint32_t acc_col = (uint32_t)slot * 256u + (uint32_t)half * 128u;
+          const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)half * 128u;
           const float* mod_l = (slot ? cur1 : cur0).mod_base + (size_t)l * layer_stride + half * 128;
           prefetch_l1(mod_l + layer_stride + (lane & 3) * 32);
+          float4 ma[4], mb[4];
+          load_mods16(mod_l, 0, ma);
           TL(3000 + l * 10 + slot);
           mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 4);
           TL(4000 + l * 10 + slot);
           tc_fence_after();
+          uint32_t va[16], vb[16];
+          tmem_ld16(tcol, va);
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            uint32_t v[32];
-            tmem_ld32(taddr_row + acc_col + j * 32, v);
-            float4 m[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = __ldg(reinterpret_cast<const float4*>(mod_l + j * 32) + i);
+          for (int hp = 0; hp < 4; ++hp) {
+            float x[16];
+            uint32_t pk[8];
             tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float h0 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 0]), P.w0) * m[i].x;
-              const float h1 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 1]), P.w0) * m[i].y;
-              const float h2 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 2]), P.w0) * m[i].z;
-              const float h3 = act_fast<ACT, W0ONE>(__uint_as_float(v[i * 4 + 3]), P.w0) * m[i].w;
-              pk[i * 2 + 0] = pack2<BF16>(h0, h1);
-              pk[i * 2 + 1] = pack2<BF16>(h2, h3);
+            tmem_ld16(tcol + (uint32_t)(hp * 2 + 1) * 16u, vb);     // next half-chunk lands while this one is processed
+            load_mods16(mod_l, hp * 2 + 1, mb);
+            as_float16(va, x);
+            act16_pack(x, ma, pk, P.w0);
+            store16(slot, hp * 2, pk);
+            tmem_ld_wait();
+            if (hp < 3) {
+              tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
+              load_mods16(mod_l, hp * 2 + 2, ma);
             }
-            store_chunk(slot, j, pk);
+            as_float16(vb, x);
+            act16_pack(x, mb, pk, P.w0);
+            store16(slot, hp * 2 + 1, pk);
           }
           tc_fence_before();
           publish(slot);

@@ -235,6 +235,39 @@ __device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14);   // version 1, no swizzle, base offset 0
 }
 
+// ---- order-pinned epilogue arithmetic -----------------------------------------------------------------------
+// The epilogue is MUFU-bound (one sine per activation, 4 lanes/clk per SM sub-partition = one warp instruction every
+// 8 cycles).  Left to itself ptxas batches the 32 MUFU.SIN of a chunk back to back and the dependent multiplies /
+// packs after them, so a warp alternates between "only MUFU" and "no MUFU" stretches and the unit idles ~30 % of the
+// time with two warps per sub-partition.  These volatile wrappers pin the program order so that the source can
+// interleave: sines of group g, then the multiplies and packs of group g-1.
+__device__ __forceinline__ float vsin(float x) {
+  float y;
+  asm volatile("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float vmul(float a, float b) {
+  float y;
+  asm volatile("mul.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
+  return y;
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t vpack2(float lo, float hi) {
+  uint32_t y;
+  if (BF16) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
+  else      asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
+  return y;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct SirenTcParams {

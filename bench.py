@@ -36,6 +36,10 @@ N_SLICES = N_VOLUMES * SLICES_PER_VOLUME                 # 10 340
 PATCHES_PER_SLICE, COORDS_PER_PATCH = 400, 576
 FLOP_PER_COORD = 4 * 2 * 256 * 256                       # tensor-eligible hidden contractions
 METRIC = "reconstructed 320x320 slices/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum of the synthesis kernel from the ncu --set full capture in
+# profiles/r01_ncu_siren_v4b.txt (132.14 MB + 40.16 MB for 64 slices); algorithmic: 400 x 5 KB of modulations read +
+# 400 x 2304 B of outputs written per slice = 2.97 MB
+DRAM_TRAFFIC_BYTES_PER_SLICE = (132.137216e6 + 40.158976e6) / 64
 MODEL_KW = dict(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=1.0, w0_initial=30.0,
                 use_bias=True, dropout=0.1, modulate=True, encoder_type="custom", encoder_path=None,
                 outer_patch_size=32, inner_patch_size=16, siren_patch_size=24)
@@ -297,8 +301,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": n_total * IMG * IMG * 4, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
-                         "kernel": "siren_tc_kernel (fused modulated-SIREN MLP)", "peak_source": f"{peak_src}, sustained bf16",
+                         "frac": achieved / peak if peak else None,
+                         "traffic": DRAM_TRAFFIC_BYTES_PER_SLICE * kern_patches / PATCHES_PER_SLICE / max(len(events), 1),
+                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_ncu_siren_v4b.txt",
+                         "kernel": "siren_tc4_kernel (fused modulated-SIREN MLP, tcgen05 cta_group::2)", "peak_source": f"{peak_src}, sustained bf16",
                          "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
                          "kernel_ms_per_step": kern_ms / args.steps, "kernel_launches_timed": len(events),
                          "kernel_share_of_step": kern_ms / ms_total},

@@ -1,0 +1,55 @@
+"""Import overlay: make the reference's own scripts (`test_mod_siren.py`, `src/util/error.py`) pick up this package
+without editing them.
+
+    import mri_inr_b200.compat as compat
+    compat.install()                      # before `import test_mod_siren` / `from src... import ...`
+
+After `install()`:
+
+* ``from src.networks.modulated_siren import ModulatedSiren`` (test_mod_siren.py:14, train_mod_siren.py:18) resolves to
+  :class:`mri_inr_b200.modulated_siren.ModulatedSiren`;
+* ``from src.util.tiling import image_to_patches, patches_to_image_weighted_average, ...`` (test_mod_siren.py:15-19,
+  src/util/error.py:14-19) resolves to :mod:`mri_inr_b200.tiling`.
+
+Everything else under ``src`` (configuration, data, error, visualization) keeps coming from the reference tree, which
+must be importable (its root on ``sys.path``) — or, when it is not, empty ``src`` / ``src.networks`` / ``src.util``
+packages are created so that the two imports above still work stand-alone.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+
+def _ensure_package(name: str) -> types.ModuleType:
+    if name in sys.modules:
+        return sys.modules[name]
+    try:
+        return importlib.import_module(name)
+    except Exception:
+        mod = types.ModuleType(name)
+        mod.__path__ = []  # type: ignore[attr-defined]
+        sys.modules[name] = mod
+        parent, _, child = name.rpartition(".")
+        if parent:
+            setattr(_ensure_package(parent), child, mod)
+        return mod
+
+
+def install() -> None:
+    from . import modulated_siren, tiling
+
+    for pkg in ("src", "src.networks", "src.util"):
+        _ensure_package(pkg)
+    sys.modules["src.networks.modulated_siren"] = modulated_siren
+    sys.modules["src.util.tiling"] = tiling
+    setattr(sys.modules["src.networks"], "modulated_siren", modulated_siren)
+    setattr(sys.modules["src.util"], "tiling", tiling)
+
+
+def uninstall() -> None:
+    for name in ("src.networks.modulated_siren", "src.util.tiling"):
+        mod = sys.modules.get(name)
+        if mod is not None and mod.__name__.startswith("mri_inr_b200."):
+            del sys.modules[name]

@@ -277,3 +277,57 @@ def test_full_size_properties():
     assert float(y.abs().max()) <= 1.0
     want = osiren.model_forward(sd, patches.cpu(), activation=act).numpy()
     assert np.abs(y.cpu().numpy() - want).max() <= 1e-3
+
+
+def test_psnr_ssim_within_north_star_tolerance():
+    """north_star acceptance: PSNR within 0.05 dB and SSIM within 1e-3 of the reference fp32 path on identical
+    weights and inputs (synthetic 320x320 single-coil k-space slices, acc 6 / cf 0.05); metrics as in
+    src/util/error.py:249-269 (scipy restatement of skimage, oracle/metrics.py)."""
+    from oracle import flow, metrics
+    from mri_inr_b200.pipeline import ReconstructionPipeline
+    from mri_inr_b200.synthetic import synthetic_slices
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    under = synthetic_slices(2, 320, 320, device=DEV, seed=77, undersampled=True)
+    full = synthetic_slices(2, 320, 320, device=DEV, seed=77, undersampled=False)
+    rec = ReconstructionPipeline(m).reconstruct(under).cpu().numpy()
+    torch.set_num_threads(8)
+    for i in range(2):
+        want = flow.reconstruct_slice(sd, under[i].cpu(), activation=act).numpy()
+        ref_img = full[i].cpu().numpy()
+        assert np.abs(rec[i] - want).max() <= 1e-3
+        assert abs(metrics.psnr(ref_img, rec[i]) - metrics.psnr(ref_img, want)) <= 0.05
+        assert abs(metrics.ssim(ref_img, rec[i]) - metrics.ssim(ref_img, want)) <= 1e-3
+        assert abs(metrics.nrmse(ref_img, rec[i]) - metrics.nrmse(ref_img, want)) <= 1e-3
+
+
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
+def test_earlier_kernel_variants_still_agree(variant):
+    """The single-CTA kernels (v1, v2) and the chunk-chasing pair kernel (v3) are kept for A/B measurements; they must
+    stay correct.  The variant is latched per process, so run them in a subprocess."""
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, '.')\n"
+        "from oracle import siren as o\n"
+        "from oracle.synth import synth_tiles\n"
+        "from tests.test_gpu_parity import _model, MODEL_CASES\n"
+        "n, kw, act, mk = MODEL_CASES[1]\n"
+        "m, sd = _model(kw, act, mk, 'fp16')\n"
+        "t = synth_tiles(9, 23)\n"
+        "with torch.no_grad():\n"
+        "    y = m(torch.from_numpy(t).cuda()).cpu().numpy()\n"
+        "want = o.model_forward(sd, torch.from_numpy(t), activation=act).numpy()\n"
+        "err = float(np.abs(y - want).max())\n"
+        "print('ERR', err)\n"
+        "assert err <= 1e-3\n"
+    )
+    import os
+
+    env = dict(os.environ, MRINR_TC_VARIANT=variant)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

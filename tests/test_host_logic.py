@@ -1,0 +1,156 @@
+"""CPU: host-side mirror of the reference interface (no GPU, no kernels)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import siren as osiren
+
+KW = dict(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=1.0, w0_initial=30.0, use_bias=True,
+          dropout=0.1, modulate=True, encoder_type="custom", encoder_path=None, outer_patch_size=32,
+          inner_patch_size=16, siren_patch_size=24, device=torch.device("cpu"), activation="sine")
+
+
+def make(**over):
+    from mri_inr_b200.modulated_siren import ModulatedSiren
+
+    kw = dict(KW)
+    kw.update(over)
+    return ModulatedSiren(**kw)
+
+
+def test_ctor_takes_the_17_reference_kwargs_and_sets_attributes():
+    m = make()
+    for name in ("dim_hidden", "dim_out", "num_layers", "latent_dim", "modulate", "encoder_type", "outer_patch_size",
+                 "inner_patch_size", "siren_patch_size", "activation", "net", "modulator", "encoder", "grid"):
+        assert hasattr(m, name), name
+    with pytest.raises(TypeError):
+        make(bogus=1)
+
+
+def test_state_dict_layout_matches_reference():
+    m = make()
+    sd = m.state_dict()
+    assert list(sd.keys()) == osiren.state_dict_key_order()
+    assert len(sd) == 31
+    assert sum(p.numel() for p in m.parameters()) == 1007873
+    assert tuple(sd["grid"].shape) == (576, 2)
+    assert tuple(sd["modulator.layers.1.0.weight"].shape) == (256, 512)
+    assert tuple(sd["encoder.encoder.encoder.4.weight"].shape) == (64, 32, 8, 8)
+    nb = make(use_bias=False).state_dict()
+    assert list(nb.keys()) == osiren.state_dict_key_order(use_bias=False)
+
+
+def test_strict_load_of_reference_state_dict():
+    m = make()
+    sd = osiren.synth_state_dict(3)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(m.net.layers[2].weight, sd["net.layers.2.weight"])
+    bad = dict(sd)
+    bad.pop("grid")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+
+
+def test_grid_buffer_bit_exact(golden):
+    from mri_inr_b200.modulated_siren import make_grid_host
+
+    for s in (8, 16, 24, 32, 48):
+        assert np.array_equal(make_grid_host(s).numpy().view(np.uint32), golden["grid_weights"][f"grid_{s}"].view(np.uint32))
+    assert np.array_equal(make().grid.numpy(), golden["grid_weights"]["grid_buffer_24"])
+
+
+def test_init_ranges_follow_reference():
+    torch.manual_seed(0)
+    m = make()
+    assert float(m.net.layers[0].weight.abs().max()) <= 0.5              # U(+-1/dim_in)
+    b = np.sqrt(6.0 / 256.0)
+    assert float(m.net.layers[1].weight.abs().max()) <= b + 1e-6         # U(+-sqrt(6/dim)/w0)
+    assert float(m.net.layers[1].weight.abs().max()) > 0.9 * b
+    assert float(m.net.last_layer.bias.abs().max()) <= b + 1e-6
+
+
+def test_weight_matrix_bit_exact(golden):
+    from mri_inr_b200.tiling import generate_weight_matrix
+
+    for k in (16, 24, 32):
+        assert np.array_equal(generate_weight_matrix(k).numpy().view(np.uint32),
+                              golden["grid_weights"][f"weights_{k}"].view(np.uint32))
+
+
+def test_no_cpu_path_and_inference_only():
+    m = make().eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 32, 32))
+    m.train()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="eval"):
+        m(torch.zeros(2, 32, 32))
+    from mri_inr_b200 import ops
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.image_to_patches(torch.zeros(1, 64, 64), 32, 16)
+
+
+def test_out_of_scope_encoder_is_refused():
+    with pytest.raises(NotImplementedError):
+        make(encoder_type="vgg")
+
+
+def test_fixed_encoder_loads_reference_checkpoint_format():
+    """FixedEncoder reads {"state_dict": FixedAutoencoder.state_dict()} (siren_encoder.py:544-549): encoder.* keys are
+    used, decoder.* keys ignored."""
+    sd = osiren.synth_state_dict(5)
+    p = "encoder.encoder.encoder."
+    ckpt = {"encoder." + k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+    ckpt["decoder.0.weight"] = torch.zeros(64, 256)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "custom_encoder.pth")
+        torch.save({"state_dict": ckpt}, path)
+        m = make(encoder_path=path)
+    assert torch.equal(m.encoder.encoder.encoder[7].weight, sd[p + "7.weight"])
+    # the encoder forward (PyTorch submodule) equals the oracle restatement
+    tiles = torch.rand(3, 32, 32)
+    with torch.no_grad():
+        z = m.encoder(tiles)
+    assert torch.allclose(z, osiren.encoder_forward(sd, tiles), atol=1e-6)
+
+
+def test_shard_range_partitions_every_item_once():
+    from mri_inr_b200.dist import shard_counts, shard_range
+
+    for n in (0, 1, 7, 10340):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+            assert shard_counts(n, world) == [e - s for s, e in spans]
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_column_mask_statistics():
+    from mri_inr_b200.synthetic import column_mask
+
+    m = column_mask(320, 6, 0.05, 1234)
+    assert m.dtype == bool and m.shape == (320,)
+    assert m[152:168].all()                       # 16 centre columns (round(320*0.05))
+    assert 30 <= m.sum() <= 80                    # ~320/6 = 53 columns expected
+
+
+def test_import_overlay_redirects_reference_imports():
+    """`from src.networks.modulated_siren import ModulatedSiren` (test_mod_siren.py:14) resolves to this package."""
+    import subprocess
+    import sys
+
+    code = ("import mri_inr_b200.compat as c; c.install();"
+            "from src.networks.modulated_siren import ModulatedSiren;"
+            "from src.util.tiling import image_to_patches, patches_to_image_weighted_average, patches_to_image, "
+            "filter_and_remember_black_patches, reintegrate_black_patches;"
+            "import mri_inr_b200.modulated_siren as m; assert ModulatedSiren is m.ModulatedSiren; print('ok')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr

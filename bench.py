@@ -111,6 +111,7 @@ def cpu_reference_rate(sd, slices_cpu, activation, n_warm=1, budget_s=20.0, max_
 
     from oracle import flow
 
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
     for i in range(n_warm):
         flow.reconstruct_slice(sd, slices_cpu[i % len(slices_cpu)], activation=activation)
     t0, n = time.perf_counter(), 0
@@ -128,6 +129,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
     from mri_inr_b200.synthetic import column_mask  # noqa: F401  (host-only helper; no GPU needed here)
     import numpy as np
 

@@ -177,6 +177,74 @@ modulator_kernel(const float* __restrict__ latent, long long B, int Z, int H, in
   }
 }
 
+// ---- modulator, register-tiled version (H == 256, Z <= 256): 64 patches per CTA, 8 x 8 outputs per thread -------
+// Activations live in shared memory as [k][patch] (row stride 68 floats) so that the 8 patch values a thread needs
+// for one k are two 16-byte broadcast loads; a thread's 8 output columns are tx + 32 j so that its weight loads
+// (wT[k][col]) and its global stores are 128-byte coalesced per warp.  64 FFMA per 2 LDS.128 + 8 LDG.
+constexpr int MT_P = 64;        // patches per CTA
+constexpr int MT_LD = 68;       // smem row stride (floats)
+
+__global__ void __launch_bounds__(256, 1)
+modulator_tiled_kernel(const float* __restrict__ latent, long long B, int Z, int L,
+                       const float* __restrict__ wT, const float* __restrict__ bias, float* __restrict__ mods) {
+  constexpr int H = 256;
+  extern __shared__ __align__(16) float smem[];
+  float* s_z = smem;                       // [Z][68]
+  float* s_h0 = smem + 256 * MT_LD;        // [256][68]
+  float* s_h1 = s_h0 + 256 * MT_LD;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long p0 = (long long)blockIdx.x * MT_P;
+  // latent [patch][Z] -> s_z[k][patch]
+  for (int i = threadIdx.x; i < MT_P * Z; i += 256) {
+    const int p = i / Z, k = i - p * Z;
+    s_z[k * MT_LD + p] = (p0 + p < B) ? latent[(p0 + p) * Z + k] : 0.f;
+  }
+  __syncthreads();
+  const float* w = wT;
+  for (int l = 0; l < L; ++l) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const float* s_prev = (l & 1) ? s_h0 : s_h1;     // layer l-1 wrote buffer (l-1)&1: 0 -> s_h0, 1 -> s_h1
+    float* s_next = (l & 1) ? s_h1 : s_h0;
+    const int n_seg = (l == 0) ? 1 : 2;
+    for (int seg = 0; seg < n_seg; ++seg) {
+      const bool zseg = (l == 0) || (seg == 1);        // cat((h, z)): hidden first, then latent (:341)
+      const float* s_in = zseg ? s_z : s_prev;
+      const int K = zseg ? Z : H;
+#pragma unroll 2
+      for (int k = 0; k < K; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(s_in + k * MT_LD + ty * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(s_in + k * MT_LD + ty * 8 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = __ldg(w + (long long)k * H + tx + 32 * j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      w += (long long)K * H;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = tx + 32 * j;
+      const float bj = bias[l * H + col];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = fmaxf(acc[i][j] + bj, 0.f);
+        const int p = ty * 8 + i;
+        s_next[col * MT_LD + p] = v;
+        if (p0 + p < B) mods[((long long)l * B + p0 + p) * H + col] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- exact-mode synthesis kernel: SirenNet.forward, modulated_siren.py:215-233 -------------------------
 // smem: h [2][TM][H] | row bookkeeping
 __global__ void __launch_bounds__(512)
@@ -308,6 +376,19 @@ extern "C" int mrinr_modulator_forward(const MrinrPacked* p, const float* d_late
   MRINR_REQUIRE(p && d_latent && d_mods, MRINR_E_ARG, "mrinr_modulator_forward: null pointer");
   MRINR_REQUIRE(B >= 0, MRINR_E_ARG, "mrinr_modulator_forward: negative batch");
   if (B == 0) return 0;
+  if (p->H == 256 && p->Z <= 256) {
+    const size_t smem_t = (size_t)3 * 256 * MT_LD * sizeof(float);
+    static bool configured_t = false;
+    if (!configured_t) {
+      MRINR_CUDA(cudaFuncSetAttribute(modulator_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      configured_t = true;
+    }
+    const long long grid_t = (B + MT_P - 1) / MT_P;
+    modulator_tiled_kernel<<<(unsigned)grid_t, 256, smem_t, (cudaStream_t)stream>>>(d_latent, B, p->Z, p->L, p->d_mod_wT,
+                                                                                  p->d_mod_bias, d_mods);
+    count_launch();
+    return check_launch("modulator_tiled");
+  }
   const size_t smem = ((size_t)TM * p->Z + (size_t)2 * TM * p->H) * sizeof(float);
   static int configured_for = -1;
   if (configured_for != (int)smem) {

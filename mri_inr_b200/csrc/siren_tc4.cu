@@ -36,7 +36,13 @@ constexpr int kSlabBytes = 16384;    // K=64 x N=128 (this CTA's half of the out
 constexpr int kBiasSlabBytes = 4096; // K=16 x N=128 x 2 B
 constexpr int kNumSlabs = 5;         // 4 weight slabs + the bias step
 constexpr int kLayerBytes = 4 * kSlabBytes + kBiasSlabBytes;   // per (layer, rank) in the packed array
-constexpr int kEpiWarps = 8;
+#ifndef MRINR_EPI_WARPS
+#define MRINR_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = MRINR_EPI_WARPS;     // 8 or 16: 2 or 4 epilogue warps per SM sub-partition
+constexpr int kColGroups = kEpiWarps / 4;      // a warp owns rows 32(w&3)..+31 and columns [kCols*(w>>2), +kCols)
+constexpr int kCols = 256 / kColGroups;        // 128 or 64 columns per thread per phase
+constexpr int kPairs = kCols / 32;             // pairs of 16-column half-chunks per phase
 constexpr int kThreads = kEpiWarps * 32 + 64;
 constexpr int kMaxLayers = 16;
 constexpr int kTmemCols = 512;
@@ -46,8 +52,8 @@ constexpr int kOffOnes = 2 * 65536;                               // [2 kc][128]
 constexpr int kOffW = kOffOnes + 4096;                            // 4 x 16 KB + 4 KB
 constexpr int kOffL0 = kOffW + kLayerBytes;                       // [3][256] f32
 constexpr int kOffLastW = kOffL0 + 3 * kH * 4;                    // [256] f32
-constexpr int kOffPart = kOffLastW + kH * 4;                      // [2][128] f32
-constexpr int kOffBar = kOffPart + 2 * kTileM * 4;
+constexpr int kOffPart = kOffLastW + kH * 4;                      // [2 slots][3 column groups][128] f32 partial dots
+constexpr int kOffBar = kOffPart + 2 * 3 * kTileM * 4;
 constexpr int kOffTmemPtr = kOffBar + 32 * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 
@@ -58,23 +64,33 @@ constexpr int kBarAFull = 15;    // [2] leader: 16 warp arrivals (8 warps x 2 CT
 constexpr int kBarAccFull = 17;  // [2] both CTAs, via multicast commit
 
 #ifdef MRINR_TIMELINE
-// development aid: per-phase timestamps of one warp (see tools/timeline.py); compiled out by default
+// development aid: per-phase timestamps of one lane per selected warp (see tools/timeline.py); compiled out by
+// default.  Timestamps are kept in a per-thread local array and written out once at the end (no atomics in the loop).
 __device__ long long g_timeline[8192];
 __device__ int g_timeline_n;
+#define TL_DECL long long tl_buf[160]; int tl_tag[160]; int tl_n = 0;
 #define TL(tag)                                                                          \
   do {                                                                                   \
-    if (lane == 0 && (warp == 0 || warp == 5 || warp == 8) && blockIdx.x < 2) {           \
-      const int _i = atomicAdd(&g_timeline_n, 1);                                        \
-      if (_i < 2048) {                                                                   \
-        g_timeline[_i * 4 + 0] = (long long)blockIdx.x * 100 + warp;                     \
-        g_timeline[_i * 4 + 1] = (tag);                                                  \
-        g_timeline[_i * 4 + 2] = clock64();                                              \
-        g_timeline[_i * 4 + 3] = 0;                                                      \
+    if (lane == 0 && blockIdx.x == 0 && (warp == 0 || warp == kEpiWarps) && tl_n < 160) { \
+      tl_buf[tl_n] = clock64(); tl_tag[tl_n] = (tag); ++tl_n;                             \
+    }                                                                                    \
+  } while (0)
+#define TL_FLUSH                                                                          \
+  do {                                                                                   \
+    if (lane == 0 && blockIdx.x == 0 && (warp == 0 || warp == kEpiWarps)) {               \
+      const int base = atomicAdd(&g_timeline_n, tl_n);                                   \
+      for (int _i = 0; _i < tl_n && base + _i < 2048; ++_i) {                             \
+        g_timeline[(base + _i) * 4 + 0] = warp;                                          \
+        g_timeline[(base + _i) * 4 + 1] = tl_tag[_i];                                    \
+        g_timeline[(base + _i) * 4 + 2] = tl_buf[_i];                                    \
+        g_timeline[(base + _i) * 4 + 3] = 0;                                             \
       }                                                                                  \
     }                                                                                    \
   } while (0)
 #else
+#define TL_DECL
 #define TL(tag) do { } while (0)
+#define TL_FLUSH do { } while (0)
 #endif
 
 struct RowInfo {
@@ -139,11 +155,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  TL_DECL
 
   if (warp < kEpiWarps) {
     // =========================== epilogue warps (both CTAs, identical) ===========================
     const int q = warp & 3;
-    const int half = warp >> 2;
+    const int half = warp >> 2;        // column group (name kept from the 2-group version)
     const int t = q * 32 + lane;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
     const float last_b = P.last_b ? *P.last_b : 0.f;
@@ -186,7 +203,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       }
     };
     auto store16 = [&](int slot, int hc, const uint32_t (&pk)[8]) {   // columns half*128 + hc*16 .. +15 of row t
-      uint8_t* base = smem + kOffA + slot * 65536 + (half * 16 + hc * 2) * 2048 + t * 16;
+      uint8_t* base = smem + kOffA + slot * 65536 + (half * (kCols / 8) + hc * 2) * 2048 + t * 16;
       *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(base + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     };
@@ -201,9 +218,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 
     // output phase of a finished tile: y = sin(w0 (h_{L-1} . w_last + b_last)), h_{L-1} = act(D) * mod
     auto final_phase = [&](int slot, const RowInfo& ri, uint32_t ev) {
-      const float* mod_l = ri.mod_base + (size_t)(L - 1) * layer_stride + half * 128;
-      const float* lw = s_lastw + half * 128;
-      const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)half * 128u;
+      const float* mod_l = ri.mod_base + (size_t)(L - 1) * layer_stride + half * kCols;
+      const float* lw = s_lastw + half * kCols;
+      const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)(half * kCols);
       float4 ma[4], mb[4];
       load_mods16(mod_l, 0, ma);
       TL(1000 + slot);
@@ -234,27 +251,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         }
       };
 #pragma unroll 1
-      for (int hp = 0; hp < 4; ++hp) {
+      for (int hp = 0; hp < kPairs; ++hp) {
         tmem_ld_wait();
         tmem_ld16(tcol + (uint32_t)(hp * 2 + 1) * 16u, vb);
         load_mods16(mod_l, hp * 2 + 1, mb);
         dot16(va, ma, hp * 2);
         tmem_ld_wait();
-        if (hp < 3) {
+        if (hp < kPairs - 1) {
           tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
           load_mods16(mod_l, hp * 2 + 2, ma);
         }
         dot16(vb, mb, hp * 2 + 1);
       }
       tc_fence_before();
-      float* part = s_part + slot * kTileM;
-      if (half == 1) {
-        part[t] = dot;
-        asm volatile("bar.arrive %0, 64;" ::"r"(2 + q) : "memory");
+      // combine the column groups of a row: groups 1.. hand their partial dot to group 0's warp of the same quarter
+      float* part = s_part + slot * 3 * kTileM;
+      if (half != 0) {
+        part[(half - 1) * kTileM + t] = dot;
+        asm volatile("bar.arrive %0, %1;" ::"r"(2 + q), "r"(32 * kColGroups) : "memory");
       } else {
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(32 * kColGroups) : "memory");
+#pragma unroll
+        for (int gq = 0; gq < kColGroups - 1; ++gq) dot += part[gq * kTileM + t];
         // output layer: always sine, never modulated (modulated_siren.py:211-213, :233)
-        if (ri.out != nullptr) *ri.out = sinf(P.w0 * (dot + part[t] + last_b));
+        if (ri.out != nullptr) *ri.out = sinf(P.w0 * (dot + last_b));
       }
     };
 
@@ -299,11 +319,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         if (slot) cur1 = my; else cur0 = my;
         TL(2000 + slot);
         // layer 0 (modulated_siren.py:154-156 with dim_in = 2): h = act(w0_initial (W0 g + b0)) * mod_0
-        const float* mod_l = my.mod_base + half * 128;
-        prefetch_l1(mod_l + layer_stride + (lane & 3) * 32);
-        const float* wa = s_l0 + half * 128;
-        const float* wb = s_l0 + kH + half * 128;
-        const float* wc = s_l0 + 2 * kH + half * 128;
+        const float* mod_l = my.mod_base + half * kCols;
+        prefetch_l1(mod_l + layer_stride + (lane % (kCols / 32)) * 32);
+        const float* wa = s_l0 + half * kCols;
+        const float* wb = s_l0 + kH + half * kCols;
+        const float* wc = s_l0 + 2 * kH + half * kCols;
         float4 ma[4], mb[4];
         load_mods16(mod_l, 0, ma);
         auto layer0_16 = [&](int hc, const float4 (&m)[4]) {
@@ -346,10 +366,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           store16(slot, hc, pk);
         };
 #pragma unroll 1
-        for (int hp = 0; hp < 4; ++hp) {
+        for (int hp = 0; hp < kPairs; ++hp) {
           load_mods16(mod_l, hp * 2 + 1, mb);
           layer0_16(hp * 2, ma);
-          if (hp < 3) load_mods16(mod_l, hp * 2 + 2, ma);
+          if (hp < kPairs - 1) load_mods16(mod_l, hp * 2 + 2, ma);
           layer0_16(hp * 2 + 1, mb);
         }
         publish(slot);
@@ -364,9 +384,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         const uint32_t ev = ev0 + (uint32_t)(l - 1);
 #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
-          const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)half * 128u;
-          const float* mod_l = (slot ? cur1 : cur0).mod_base + (size_t)l * layer_stride + half * 128;
-          prefetch_l1(mod_l + layer_stride + (lane & 3) * 32);
+          const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)(half * kCols);
+          const float* mod_l = (slot ? cur1 : cur0).mod_base + (size_t)l * layer_stride + half * kCols;
+          prefetch_l1(mod_l + layer_stride + (lane % (kCols / 32)) * 32);
           float4 ma[4], mb[4];
           load_mods16(mod_l, 0, ma);
           TL(3000 + l * 10 + slot);
@@ -376,7 +396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           uint32_t va[16], vb[16];
           tmem_ld16(tcol, va);
 #pragma unroll 1
-          for (int hp = 0; hp < 4; ++hp) {
+          for (int hp = 0; hp < kPairs; ++hp) {
             float x[16];
             uint32_t pk[8];
             tmem_ld_wait();
@@ -386,7 +406,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
             act16_pack(x, ma, pk, P.w0);
             store16(slot, hp * 2, pk);
             tmem_ld_wait();
-            if (hp < 3) {
+            if (hp < kPairs - 1) {
               tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
               load_mods16(mod_l, hp * 2 + 2, ma);
             }
@@ -493,6 +513,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     __syncwarp();
   }
 
+  TL_FLUSH;
   // ---- teardown: both CTAs must be done before the pair's TMEM is released ----
   tc_fence_before();
   __syncthreads();

@@ -23,6 +23,6 @@ t0 = min(e[2] for e in ev)
 for who in sorted(set(e[0] for e in ev)):
     print("== cta*100+warp", who)
     prev = None
-    for w, tag, t in sorted([e for e in ev if e[0] == who], key=lambda x: x[2])[:90]:
+    for w, tag, t in sorted([e for e in ev if e[0] == who], key=lambda x: x[2])[:150]:
         print(f"  {tag:5d}  t={t - t0:8d}  dt={(t - prev) if prev else 0:7d}")
         prev = t

@@ -12,7 +12,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmrinr.so")
+# MRINR_LIB: development override (an instrumented build of the same library, e.g. build/libmrinr_tl.so)
+LIB_PATH = os.environ.get("MRINR_LIB") or os.path.join(_HERE, "lib", "libmrinr.so")
 
 # include/mrinr.h
 ABI_VERSION = 1

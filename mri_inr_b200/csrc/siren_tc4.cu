@@ -63,7 +63,7 @@ constexpr int kBarWEmpty = 10;   // [5] both CTAs, via multicast commit
 constexpr int kBarAFull = 15;    // [2] leader: 16 warp arrivals (8 warps x 2 CTAs): operand of slot s complete
 constexpr int kBarAccFull = 17;  // [2] both CTAs, via multicast commit
 
-#ifdef MRINR_TIMELINE
+#ifdef MRINR_TIMELINE_V4
 // development aid: per-phase timestamps of one lane per selected warp (see tools/timeline.py); compiled out by
 // default.  Timestamps are kept in a per-thread local array and written out once at the end (no atomics in the loop).
 __device__ long long g_timeline[8192];
@@ -567,7 +567,7 @@ int launch_siren_tc_v4(const MrinrPacked* p, const float* d_mods, const int32_t*
 }  // namespace v4
 }  // namespace mrinr
 
-#ifdef MRINR_TIMELINE
+#ifdef MRINR_TIMELINE_V4
 extern "C" __attribute__((visibility("default"))) int mrinr_debug_timeline(long long* host_out, int max_entries) {
   int n = 0;
   cudaMemcpyFromSymbol(&n, mrinr::v4::g_timeline_n, sizeof(int));

@@ -32,7 +32,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-static __device__ __noinline__ void mbar_timeout(int32_t* errflag, int code) {
+static __device__ __noinline__ __attribute__((noreturn)) void mbar_timeout(int32_t* errflag, int code) {
   if (errflag) atomicExch(errflag, code);
   __trap();
 }
@@ -134,6 +134,28 @@ __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// fp32-accurate sine without the library's slow path (a call that forces every live register to be spilled around
+// it): three-term Cody-Waite reduction by pi/2 + degree-9 / degree-8 minimax polynomials.  |error| <= ~1 ulp for
+// |x| <= 1e4 (the output pre-activation is O(1)); beyond that the reduction loses bits gradually instead of
+// switching to Payne-Hanek.
+__device__ __forceinline__ float sin_accurate(float x) {
+  const float qf = rintf(x * 0.636619772367581343f);
+  const int k = (int)qf;
+  float r = fmaf(qf, -1.57079601287841796875f, x);
+  r = fmaf(qf, -3.13916473151482683e-7f, r);
+  r = fmaf(qf, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  float ps = fmaf(r2, 2.60831598e-6f, -1.98106907e-4f);
+  ps = fmaf(ps, r2, 8.33307858e-3f);
+  ps = fmaf(ps, r2, -1.66666597e-1f);
+  const float sn = fmaf(ps * r2, r, r);
+  float pc = fmaf(r2, 2.44331568e-5f, -1.38873163e-3f);
+  pc = fmaf(pc, r2, 4.16666418e-2f);
+  pc = fmaf(pc, r2, -0.5f);
+  const float cs = fmaf(pc, r2, 1.0f);
+  const float v = (k & 1) ? cs : sn;
+  return (k & 2) ? -v : v;
 }
 template <int ACT, bool W0ONE>
 __device__ __forceinline__ float act_fast(float x, float w0) {

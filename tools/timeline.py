@@ -1,4 +1,7 @@
-"""Development aid: phase timeline of the v4 synthesis kernel (library built with EXTRA=-DMRINR_TIMELINE)."""
+"""Development aid: phase timeline of the synthesis kernel.
+
+    make -C mri_inr_b200/csrc timeline && MRINR_LIB=build/libmrinr_tl.so python tools/timeline.py
+"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -41,6 +41,8 @@ constexpr int kColGroups = kEpiWarps / 4;      // a warp owns rows 32(w&3)..+31 
 constexpr int kCols = 256 / kColGroups;        // 128 or 64 columns per thread per phase
 constexpr int kPairs = kCols / 32;             // pairs of 16-column chunks per phase
 constexpr int kThreads = kEpiWarps * 32 + 64;
+// Register budget: the register file is split per SM sub-partition (16 384 each) and the 10 (18) warps of the CTA
+// land 3 (5) on some sub-partition, so the cap is 168 (96) registers per thread -- not 65536 / kThreads.
 constexpr int kMaxLayers = 16;
 constexpr int kTmemCols = 512;
 constexpr int kMaxSub = 2;                     // patches sharing a remainder tile
@@ -207,35 +209,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     const int t = q * 32 + lane;       // tile row == TMEM lane
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
     const float last_b = P.last_b ? *P.last_b : 0.f;
+    const float w_mine = P.last_w[tid & (kH - 1)];   // output-layer weight of the column this thread pre-scales
 
     // per coordinate block (changes C/128 + 1 times per launch)
     int cur_type = -1;
     int c_row = 0;                     // this row's coordinate within the patch
     int sub_row = 0;                   // which of the tile's patches this row belongs to (remainder block only)
+    int sub_prev = 0;                  // sub_row of the previous iteration's tiles (their output phase runs late)
     bool row_live = false;             // false: padding row of a remainder tile
     uint32_t T2[kCols / 2];            // layer-0 table of (c_row, this thread's columns), packed pairs
+    float* out0 = nullptr; float* out1 = nullptr;      // output element of this row for the tile in slot 0 / 1
 
-    float* out0 = nullptr; float* out1 = nullptr;      // output element of this row for the tiles in slot 0 / 1
-    float* pout0 = nullptr; float* pout1 = nullptr;    // ... of the previous iteration's tiles
-    bool have_prev = false;
-
-    int sub_prev = 0;                  // sub_row of the previous iteration's tiles (their output phase runs late)
-    auto mod_ptr = [&](int slot, uint32_t use, int sub) -> const float* {
-      return s_mods + ((((use & (kModStages - 1)) * 2 + slot) * kMaxSub + sub) * kH + cg * kCols);
+    auto mod_stage = [&](int slot, uint32_t use) -> float* {
+      return s_mods + (((use & (kModStages - 1)) * 2 + slot) * kMaxSub) * kH;
+    };
+    auto mod_full_bar = [&](int slot, uint32_t use) -> uint32_t {
+      return bar(kBarModFull + slot * kModStages + (int)(use & (kModStages - 1)));
+    };
+    // non-blocking probe, issued early so that its latency (~100 cycles) hides behind other work; the modulation
+    // vectors are requested several phases ahead, so the probe almost always succeeds
+    auto peek_mods = [&](int slot, uint32_t use) -> uint32_t {
+      return mbar_try_wait(mod_full_bar(slot, use), (use / kModStages) & 1u);
     };
     auto wait_mods = [&](int slot, uint32_t use) {
-      mbar_wait(bar(kBarModFull + slot * kModStages + (use & (kModStages - 1))), (use / kModStages) & 1u, P.errflag, 6);
+      mbar_wait(mod_full_bar(slot, use), (use / kModStages) & 1u, P.errflag, 6);
     };
     // this warp is done with the phase: its part of A[slot] is written (publish_a) and its modulation reads are over
     auto finish_phase = [&](int slot, uint32_t use, bool publish_a) {
-      if (publish_a) fence_proxy_async();
+      fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar(kBarModEmpty + slot * kModStages + (use & (kModStages - 1))));
+        mbar_arrive(bar(kBarModEmpty + slot * kModStages + (int)(use & (kModStages - 1))));
         if (publish_a) mbar_arrive_cluster(bar(kBarAFull + slot), 0);
       }
     };
-    auto load_mods16 = [&](const float* mp, int hc, float4 (&m)[4]) {
+    auto load4x4 = [&](const float* mp, int hc, float4 (&m)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const float4*>(mp + hc * 16 + i * 4);
     };
@@ -275,25 +283,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       *reinterpret_cast<uint4*>(base + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     };
 
-    // output phase of a finished tile: y = sin(w0 (h_{L-1} . w_last + b_last)), h_{L-1} = act(D) * mod
+    // output phase of a finished tile: y = sin(w0 (h_{L-1} . w_last + b_last)), h_{L-1} = act(D) * mod_{L-1}.
+    // All rows of a tile share the modulation vector, so the epilogue threads first turn the ring stage into
+    // mod_{L-1} * w_last in place (one or two elements per thread); a row then needs one FFMA per activation.
     auto final_phase = [&](int slot, float* outp, uint32_t ev, uint32_t use) {
-      const float* lw = s_lastw + cg * kCols;
       const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)(cg * kCols);
       TL(1000 + slot);
       wait_mods(slot, use);
-      const float* mp = mod_ptr(slot, use, sub_prev);
+      float* ring = mod_stage(slot, use);
+#pragma unroll
+      for (int j = tid; j < kMaxSub * kH; j += kEpiWarps * 32) ring[j] *= w_mine;
+      named_bar_sync(1, kEpiWarps * 32);
+      const float* mp = ring + sub_prev * kH + cg * kCols;
       mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 5);
       TL(1010 + slot);
       tc_fence_after();
       uint32_t va[16], vb[16];
       tmem_ld16(tcol, va);
-      float dot = 0.f;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
       auto dot16 = [&](const uint32_t (&v)[16], int hc) {
-        float4 m[4];
-        load_mods16(mp, hc, m);
+        float4 mw[4];
+        load4x4(mp, hc, mw);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float4 w = *reinterpret_cast<const float4*>(lw + hc * 16 + g * 4);
           const float x0 = __uint_as_float(v[g * 4 + 0]), x1 = __uint_as_float(v[g * 4 + 1]);
           const float x2 = __uint_as_float(v[g * 4 + 2]), x3 = __uint_as_float(v[g * 4 + 3]);
           float h0, h1, h2, h3;
@@ -304,10 +316,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
             h0 = act_fast<ACT, W0ONE>(x0, P.w0); h1 = act_fast<ACT, W0ONE>(x1, P.w0);
             h2 = act_fast<ACT, W0ONE>(x2, P.w0); h3 = act_fast<ACT, W0ONE>(x3, P.w0);
           }
-          dot = fmaf(h0 * m[g].x, w.x, dot);
-          dot = fmaf(h1 * m[g].y, w.y, dot);
-          dot = fmaf(h2 * m[g].z, w.z, dot);
-          dot = fmaf(h3 * m[g].w, w.w, dot);
+          d0 = fmaf(h0, mw[g].x, d0);
+          d1 = fmaf(h1, mw[g].y, d1);
+          d2 = fmaf(h2, mw[g].z, d2);
+          d3 = fmaf(h3, mw[g].w, d3);
         }
       };
 #pragma unroll 1
@@ -321,6 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       }
       tc_fence_before();
       finish_phase(slot, use, false);
+      float dot = (d0 + d1) + (d2 + d3);
       // combine the column groups of a row: groups 1.. hand their partial dot to group 0's warp of the same quarter
       float* part = s_part + slot * 3 * kTileM;
       if (cg != 0) {
@@ -336,10 +349,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     };
 
     Walk w;
-    for (long long it = 0; it < S.total; ++it, w.next(S)) {
+    for (long long it = 0; it <= S.total; ++it) {
+      const bool last = (it == S.total);                           // extra pass: only the pending output phases
       const uint32_t use0 = (uint32_t)it * (uint32_t)L;           // modulation-ring sequence number of layer 0
       const uint32_t ev0 = (uint32_t)it * (uint32_t)(L - 1);      // accumulator event of this iteration's layer 1
-      if (w.type != cur_type) {
+      sub_prev = sub_row;
+      if (!last && w.type != cur_type) {
         // ---- new coordinate block: this row's coordinate and its slice of the layer-0 table ----
         cur_type = w.type;
         if (cur_type < S.n_full) {
@@ -361,9 +376,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         }
       }
       // ---- per slot: finish the previous tile of the slot, then write the layer-0 operand of the new one ----
-#pragma unroll
+#pragma unroll 1
       for (int slot = 0; slot < 2; ++slot) {
-        if (have_prev) final_phase(slot, slot ? pout1 : pout0, ev0 - 1u, use0 - 1u);
+        const uint32_t ok0 = last ? 1u : peek_mods(slot, use0);
+        if (it > 0) final_phase(slot, slot ? out1 : out0, ev0 - 1u, use0 - 1u);
+        if (last) continue;
         {
           // which patch does this row belong to?  (a phantom tile / padding row has no output)
           const long long ti = w.j * 4 + slot * 2 + (long long)rank;
@@ -377,13 +394,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         }
         // layer 0 (modulated_siren.py:154-156 with dim_in = 2): h = table[c] * mod_0
         TL(2000 + slot);
-        wait_mods(slot, use0);
-        const float* mp = mod_ptr(slot, use0, sub_row);
+        if (!ok0) wait_mods(slot, use0);
+        const float* mp = mod_stage(slot, use0) + sub_row * kH + cg * kCols;
         TL(2005 + slot);
 #pragma unroll
         for (int hc = 0; hc < kCols / 16; ++hc) {
           float4 m[4];
-          load_mods16(mp, hc, m);
+          load4x4(mp, hc, m);
           uint32_t pk[8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -398,6 +415,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         finish_phase(slot, use0, true);
         TL(2010 + slot);
       }
+      if (last) break;
 
       // ---- hidden layers 1 .. L-2, alternating slots: the other slot's MMAs run underneath ----
       for (int l = 1; l <= L - 2; ++l) {
@@ -407,10 +425,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         for (int slot = 0; slot < 2; ++slot) {
           const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)(cg * kCols);
           TL(3000 + l * 10 + slot);
-          wait_mods(slot, use);
-          const float* mp = mod_ptr(slot, use, sub_row);
-          TL(3500 + l * 10 + slot);
+          const uint32_t okm = peek_mods(slot, use);
           mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 4);
+          if (!okm) wait_mods(slot, use);
+          const float* mp = mod_stage(slot, use) + sub_row * kH + cg * kCols;
           TL(4000 + l * 10 + slot);
           tc_fence_after();
           uint32_t va[16], vb[16];
@@ -421,12 +439,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
             uint32_t pk[8];
             tmem_ld_wait();
             tmem_ld16(tcol + (uint32_t)(hp * 2 + 1) * 16u, vb);     // next chunk lands while this one is processed
-            load_mods16(mp, hp * 2, m);
+            load4x4(mp, hp * 2, m);
             act16_pack(va, m, pk);
             store16(slot, hp * 2, pk);
             tmem_ld_wait();
             if (hp < kPairs - 1) tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
-            load_mods16(mp, hp * 2 + 1, m);
+            load4x4(mp, hp * 2 + 1, m);
             act16_pack(vb, m, pk);
             store16(slot, hp * 2 + 1, pk);
           }
@@ -435,16 +453,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           TL(5000 + l * 10 + slot);
         }
       }
-      pout0 = out0;
-      pout1 = out1;
-      sub_prev = sub_row;
-      have_prev = true;
-    }
-    if (have_prev) {
-      const uint32_t ev_last = (uint32_t)S.total * (uint32_t)(L - 1) - 1u;
-      const uint32_t use_last = (uint32_t)S.total * (uint32_t)L - 1u;
-      final_phase(0, pout0, ev_last, use_last);
-      final_phase(1, pout1, ev_last, use_last);
+      w.next(S);
     }
   } else if (warp == kEpiWarps) {
     if (rank == 0) {

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRINR_ABI_VERSION 1
+#define MRINR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MRINR_API __attribute__((visibility("default")))
@@ -69,6 +69,18 @@ typedef struct MrinrWeightsView {
   const float* d_last_bias;        /* [1] or NULL                                                   */
   const float* const* d_mod_weight;/* host array of L device pointers: [H,Z], then [H,H+Z]          */
   const float* const* d_mod_bias;  /* host array of L device pointers [H]                           */
+  /* Patch encoder (FixedAutoencoder.encoder, src/networks/encoding/siren_encoder.py:503-512), optional: all eight
+   * pointers NULL = no encoder packed (mrinr_encoder_forward then fails with MRINR_E_ARG). */
+  int32_t outer_patch_size;        /* O; the encoder is hard-wired to 32x32 inputs (siren_encoder.py:498-512) */
+  int32_t reserved2;
+  const float* d_enc_conv1_weight; /* [16,1,3,3]  encoder.encoder.encoder.0.weight */
+  const float* d_enc_conv1_bias;   /* [16]                                         */
+  const float* d_enc_conv2_weight; /* [32,16,3,3] encoder.encoder.encoder.2.weight */
+  const float* d_enc_conv2_bias;   /* [32]                                         */
+  const float* d_enc_conv3_weight; /* [64,32,8,8] encoder.encoder.encoder.4.weight */
+  const float* d_enc_conv3_bias;   /* [64]                                         */
+  const float* d_enc_fc_weight;    /* [Z,64]      encoder.encoder.encoder.7.weight */
+  const float* d_enc_fc_bias;      /* [Z]                                          */
 } MrinrWeightsView;
 
 typedef struct MrinrPacked MrinrPacked;   /* opaque */
@@ -93,9 +105,20 @@ MRINR_API int  mrinr_packed_layer0_table(const MrinrPacked* p, float* d_out, voi
 /* d_out [S*S,2]: out[c] = (lin[c / S], lin[c % S]), lin = torch.linspace(-1,1,S).  Bit-exact. */
 MRINR_API int mrinr_make_grid(int32_t S, float* d_out, void* stream);
 
+/* ---- patch encoder: modulated_siren.py:282-301 (Encoder.forward) -> siren_encoder.py:565-577,503-512 ---------- */
+/* d_patches [B,32,32] -> d_latent [B,Z]: Conv(1,16,3,s2,p1)+LeakyReLU(.2), Conv(16,32,3,s2,p1)+LeakyReLU,
+ * Conv(32,64,8)+LeakyReLU, Flatten, Linear(64,Z).  The two strided convolutions run as fp32 FFMA, the 8x8
+ * convolution and the linear layer as split-fp16 tcgen05 products (three MMAs per product, ~1e-6 relative).
+ * d_workspace: mrinr_encoder_workspace_bytes(B) bytes, 16-byte aligned.  Tolerance vs the reference: 1e-5. */
+MRINR_API int64_t mrinr_encoder_workspace_bytes(int64_t B);
+MRINR_API int mrinr_encoder_forward(const MrinrPacked* p, const float* d_patches, int64_t B, float* d_latent,
+                          void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- modulator: modulated_siren.py:325-343 (Modulator.forward) ------------------------------------ */
 /* d_latent [B,Z] -> d_mods [L,B,H]: h_0 = relu(A_0 z + c_0), h_i = relu(A_i [h_{i-1}; z] + c_i).
- * All layers in one launch.  fp32 FFMA; tolerance vs the reference 1e-5 relative. */
+ * MRINR_PREC_FP16/BF16 with H in {64,128,256} and Z % 64 == 0: one split-fp16 tcgen05 launch per layer (three
+ * MMAs per product, fp32 accumulate, ~1e-6 relative); otherwise one fp32 FFMA launch for all layers.
+ * Tolerance vs the reference 1e-5 relative. */
 MRINR_API int mrinr_modulator_forward(const MrinrPacked* p, const float* d_latent, int64_t B, float* d_mods,
                             void* stream);
 

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MRINR_LIB") or os.path.join(_HERE, "lib", "libmrinr.so")
 
 # include/mrinr.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 ACT_SINE, ACT_MORLET = 0, 1
 PREC_FP16, PREC_BF16, PREC_FP32 = 0, 1, 2
 PRECISIONS = {"fp16": PREC_FP16, "bf16": PREC_BF16, "fp32": PREC_FP32}
@@ -26,7 +26,7 @@ ACTIVATIONS = {"sine": ACT_SINE, "morlet": ACT_MORLET}
 EXPORTED_SYMBOLS = (
     "mrinr_abi_version", "mrinr_last_error", "mrinr_launch_count",
     "mrinr_pack_weights", "mrinr_free_packed", "mrinr_packed_layer0_table",
-    "mrinr_make_grid", "mrinr_modulator_forward",
+    "mrinr_make_grid", "mrinr_encoder_workspace_bytes", "mrinr_encoder_forward", "mrinr_modulator_forward",
     "mrinr_siren_workspace_bytes", "mrinr_siren_forward",
     "mrinr_image_to_patches", "mrinr_classify_patches", "mrinr_patches_to_image",
     "mrinr_complex_abs", "mrinr_minmax_normalize",
@@ -45,6 +45,11 @@ class WeightsView(ctypes.Structure):
         ("d_net_weight", POINTER(c_void_p)), ("d_net_bias", POINTER(c_void_p)),
         ("d_last_weight", c_void_p), ("d_last_bias", c_void_p),
         ("d_mod_weight", POINTER(c_void_p)), ("d_mod_bias", POINTER(c_void_p)),
+        ("outer_patch_size", c_int32), ("reserved2", c_int32),
+        ("d_enc_conv1_weight", c_void_p), ("d_enc_conv1_bias", c_void_p),
+        ("d_enc_conv2_weight", c_void_p), ("d_enc_conv2_bias", c_void_p),
+        ("d_enc_conv3_weight", c_void_p), ("d_enc_conv3_bias", c_void_p),
+        ("d_enc_fc_weight", c_void_p), ("d_enc_fc_bias", c_void_p),
     ]
 
 
@@ -66,6 +71,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrinr_packed_layer0_table.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.mrinr_make_grid.restype = c_int
     lib.mrinr_make_grid.argtypes = [c_int32, c_void_p, c_void_p]
+    lib.mrinr_encoder_workspace_bytes.restype = c_int64
+    lib.mrinr_encoder_workspace_bytes.argtypes = [c_int64]
+    lib.mrinr_encoder_forward.restype = c_int
+    lib.mrinr_encoder_forward.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]
     lib.mrinr_modulator_forward.restype = c_int
     lib.mrinr_modulator_forward.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
     lib.mrinr_siren_workspace_bytes.restype = c_int64

@@ -55,6 +55,15 @@ extern "C" void mrinr_free_packed(MrinrPacked* p) {
   cudaFree(p->d_mod_wT);
   cudaFree(p->d_mod_bias);
   cudaFree(p->d_errflag);
+  cudaFree(p->d_mod_ws);
+  cudaFree(p->d_enc_c1w);
+  cudaFree(p->d_enc_c1b);
+  cudaFree(p->d_enc_c2w);
+  cudaFree(p->d_enc_c2b);
+  cudaFree(p->d_enc_w3s);
+  cudaFree(p->d_enc_b3);
+  cudaFree(p->d_enc_wfs);
+  cudaFree(p->d_enc_bf);
   delete p;
 }
 
@@ -183,6 +192,52 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
       PK_RC(run_transpose(v->d_mod_weight[l], H, H + Z, dst, st));
       dst += (size_t)(H + Z) * H;
     }
+    // modulator on the tensor cores: split-fp16 operands per layer (dense_tc.cu)
+    p->mod_tc = (precision != MRINR_PREC_FP32) && dense_split_supported(H, Z, 0) && dense_split_supported(H, H, Z);
+    if (p->mod_tc) {
+      PK_CUDA(cudaMalloc(&p->d_mod_ws, mod_w_elems * 2 * sizeof(uint16_t)));
+      size_t off = 0;
+      for (int l = 0; l < L; ++l) {
+        const int K = l == 0 ? Z : H + Z;
+        p->mod_ws_off[l] = off;
+        PK_RC(run_pack_split(v->d_mod_weight[l], H, K, p->d_mod_ws + off, st));
+        off += (size_t)2 * H * K;
+      }
+    }
+    // patch encoder (optional)
+    const bool any_enc = v->d_enc_conv1_weight || v->d_enc_conv1_bias || v->d_enc_conv2_weight || v->d_enc_conv2_bias ||
+                         v->d_enc_conv3_weight || v->d_enc_conv3_bias || v->d_enc_fc_weight || v->d_enc_fc_bias;
+    if (any_enc) {
+      if (!(v->d_enc_conv1_weight && v->d_enc_conv1_bias && v->d_enc_conv2_weight && v->d_enc_conv2_bias &&
+            v->d_enc_conv3_weight && v->d_enc_conv3_bias && v->d_enc_fc_weight && v->d_enc_fc_bias)) {
+        set_error("mrinr_pack_weights: the encoder needs all eight tensors (or none)");
+        rc = MRINR_E_ARG;
+        goto fail;
+      }
+      if (v->outer_patch_size != 32 || !dense_split_supported(Z, 64, 0)) {
+        set_error("mrinr_pack_weights: the encoder is hard-wired to 32x32 patches (siren_encoder.py:498-512) and needs "
+                  "latent_dim in {64,128,256} (got O=%d Z=%d)", v->outer_patch_size, Z);
+        rc = MRINR_E_UNSUPPORTED;
+        goto fail;
+      }
+      PK_CUDA(cudaMalloc(&p->d_enc_c1w, 16 * 9 * sizeof(float)));
+      PK_CUDA(cudaMalloc(&p->d_enc_c1b, 16 * sizeof(float)));
+      PK_CUDA(cudaMalloc(&p->d_enc_c2w, 32 * 16 * 9 * sizeof(float)));
+      PK_CUDA(cudaMalloc(&p->d_enc_c2b, 32 * sizeof(float)));
+      PK_CUDA(cudaMalloc(&p->d_enc_w3s, (size_t)2 * 64 * 2048 * sizeof(uint16_t)));
+      PK_CUDA(cudaMalloc(&p->d_enc_b3, 64 * sizeof(float)));
+      PK_CUDA(cudaMalloc(&p->d_enc_wfs, (size_t)2 * Z * 64 * sizeof(uint16_t)));
+      PK_CUDA(cudaMalloc(&p->d_enc_bf, (size_t)Z * sizeof(float)));
+      PK_CUDA(cudaMemcpyAsync(p->d_enc_c1w, v->d_enc_conv1_weight, 16 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PK_CUDA(cudaMemcpyAsync(p->d_enc_c1b, v->d_enc_conv1_bias, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PK_CUDA(cudaMemcpyAsync(p->d_enc_c2w, v->d_enc_conv2_weight, 32 * 16 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PK_CUDA(cudaMemcpyAsync(p->d_enc_c2b, v->d_enc_conv2_bias, 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PK_CUDA(cudaMemcpyAsync(p->d_enc_b3, v->d_enc_conv3_bias, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PK_CUDA(cudaMemcpyAsync(p->d_enc_bf, v->d_enc_fc_bias, (size_t)Z * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PK_RC(run_pack_split(v->d_enc_conv3_weight, 64, 2048, p->d_enc_w3s, st));
+      PK_RC(run_pack_split(v->d_enc_fc_weight, Z, 64, p->d_enc_wfs, st));
+      p->has_encoder = 1;
+    }
     PK_CUDA(cudaStreamSynchronize(st));
   }
   *out = p;
@@ -237,4 +292,34 @@ extern "C" int mrinr_siren_forward(const MrinrPacked* p, const float* d_mods, co
   }
   if (p->precision == MRINR_PREC_FP32) return launch_siren_fp32(p, d_mods, d_idx, d_nactive, B, d_out, st);
   return launch_siren_tc(p, d_mods, d_idx, d_nactive, B, d_out, st);
+}
+
+// ---- patch encoder ---------------------------------------------------------------------------------
+// workspace: conv2 output [B,2048] fp32 | conv3 output [B,64] fp32
+extern "C" int64_t mrinr_encoder_workspace_bytes(int64_t B) {
+  if (B < 0) return 0;
+  return (int64_t)((size_t)B * (2048 + 64) * sizeof(float));
+}
+
+extern "C" int mrinr_encoder_forward(const MrinrPacked* p, const float* d_patches, int64_t B, float* d_latent,
+                                     void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;
+  MRINR_REQUIRE(p && d_patches && d_latent, MRINR_E_ARG, "mrinr_encoder_forward: null pointer");
+  MRINR_REQUIRE(B > 0, MRINR_E_ARG, "mrinr_encoder_forward: negative batch");
+  MRINR_REQUIRE(p->has_encoder, MRINR_E_ARG, "mrinr_encoder_forward: no encoder weights were packed");
+  MRINR_REQUIRE(d_workspace && workspace_bytes >= mrinr_encoder_workspace_bytes(B), MRINR_E_ARG,
+                "mrinr_encoder_forward: needs a workspace of mrinr_encoder_workspace_bytes(B) bytes");
+  MRINR_REQUIRE(aligned16(d_patches) && aligned16(d_latent) && aligned16(d_workspace), MRINR_E_ALIGN,
+                "mrinr_encoder_forward: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* c2 = static_cast<float*>(d_workspace);
+  float* c3 = c2 + (size_t)B * 2048;
+  int rc = launch_encoder_conv(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms, st);
+  if (rc != 0) return rc;
+  // Conv2d(32,64,8) on the 8x8 map == [B,2048] x [2048,64] (weight [64,32,8,8] flattens in the same (c,y,x) order)
+  rc = launch_dense_split(c2, 2048, 2048, nullptr, 0, 0, p->d_enc_w3s, p->d_enc_b3, 64, /*leaky*/ 2, 0.2f, c3, 64, B,
+                          p->d_errflag, st);
+  if (rc != 0) return rc;
+  return launch_dense_split(c3, 64, 64, nullptr, 0, 0, p->d_enc_wfs, p->d_enc_bf, p->Z, /*none*/ 0, 0.f, d_latent, p->Z,
+                            B, p->d_errflag, st);
 }

@@ -57,6 +57,20 @@ struct MrinrPacked {
   float*    d_mod_wT;    // layer 0: [Z][H]; layer i>=1: [(H+Z)][H] -- concatenated, transposed
   float*    d_mod_bias;  // [L][H]
   int32_t*  d_errflag;   // device-side watchdog flag (mbarrier timeouts)
+  // split-fp16 tensor-core operands (dense_tc.cu): [K/64 slabs][hi, lo][8][N][8] per layer
+  uint16_t* d_mod_ws;    // modulator layers, concatenated (layer l at mod_ws_off[l], in uint16 elements)
+  size_t    mod_ws_off[17];
+  int32_t   mod_tc;      // 1: the modulator runs on the tensor cores
+  // patch encoder (optional)
+  int32_t   has_encoder;
+  float*    d_enc_c1w;   // [16,1,3,3]
+  float*    d_enc_c1b;   // [16]
+  float*    d_enc_c2w;   // [32,16,3,3]
+  float*    d_enc_c2b;   // [32]
+  uint16_t* d_enc_w3s;   // Conv2d(32,64,8) as [64, 2048], split-packed
+  float*    d_enc_b3;    // [64]
+  uint16_t* d_enc_wfs;   // Linear(64, Z), split-packed
+  float*    d_enc_bf;    // [Z]
 };
 
 namespace mrinr {
@@ -71,6 +85,13 @@ int run_pack_w16_pair(const float* w, int H, int use_bf16, uint16_t* out, cudaSt
 int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf16, uint16_t* out, cudaStream_t st);
 int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,
                      int activation, float* table, cudaStream_t st);
+bool dense_split_supported(int N, int K1, int K2);
+int run_pack_split(const float* w, int N, int K, uint16_t* out, cudaStream_t st);
+int launch_dense_split(const float* a1, long long lda1, int K1, const float* a2, long long lda2, int K2,
+                       const uint16_t* w_packed, const float* bias, int N, int act, float slope, float* c,
+                       long long ldc, long long M, int32_t* errflag, cudaStream_t st);
+int launch_encoder_conv(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,
+                        const float* b2, float* d_out, int num_sms, cudaStream_t st);
 int launch_compact_black(const uint8_t* d_black, int64_t B, int32_t C, int32_t* d_idx, int32_t* d_nactive,
                          int32_t* d_blocksums, float* d_out, cudaStream_t st);
 

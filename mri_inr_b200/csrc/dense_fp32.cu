@@ -376,6 +376,18 @@ extern "C" int mrinr_modulator_forward(const MrinrPacked* p, const float* d_late
   MRINR_REQUIRE(p && d_latent && d_mods, MRINR_E_ARG, "mrinr_modulator_forward: null pointer");
   MRINR_REQUIRE(B >= 0, MRINR_E_ARG, "mrinr_modulator_forward: negative batch");
   if (B == 0) return 0;
+  if (p->mod_tc) {
+    // tensor cores: one split-fp16 product per layer; layer l reads h_{l-1} = d_mods[l-1] and the latent
+    MRINR_REQUIRE(aligned16(d_latent) && aligned16(d_mods), MRINR_E_ALIGN, "mrinr_modulator_forward: buffers must be 16-byte aligned");
+    const size_t plane = (size_t)B * p->H;
+    int rc = launch_dense_split(d_latent, p->Z, p->Z, nullptr, 0, 0, p->d_mod_ws + p->mod_ws_off[0], p->d_mod_bias, p->H,
+                                /*relu*/ 1, 0.f, d_mods, p->H, B, p->d_errflag, (cudaStream_t)stream);
+    for (int l = 1; l < p->L && rc == 0; ++l)
+      rc = launch_dense_split(d_mods + (size_t)(l - 1) * plane, p->H, p->H, d_latent, p->Z, p->Z,
+                              p->d_mod_ws + p->mod_ws_off[l], p->d_mod_bias + (size_t)l * p->H, p->H, 1, 0.f,
+                              d_mods + (size_t)l * plane, p->H, B, p->d_errflag, (cudaStream_t)stream);
+    return rc;
+  }
   if (p->H == 256 && p->Z <= 256) {
     const size_t smem_t = (size_t)3 * 256 * MT_LD * sizeof(float);
     static bool configured_t = false;

@@ -1,0 +1,265 @@
+// Dense layers of the patch encoder and the modulator on the tensor cores, at fp32-level accuracy.
+//
+//   C[M,N] = act( [A1 | A2] . W^T + bias ),   A1 [M,K1], A2 [M,K2] fp32 row-major (A2 optional),  W [N, K1+K2]
+//
+// covers Conv2d(32,64,8) on an 8x8 map (a [B,2048] x [2048,64] product), Linear(64,Z) (siren_encoder.py:503-512) and
+// every Modulator layer, relu(A_l cat(h_{l-1}, z) + c_l) (modulated_siren.py:325-343; the hidden columns of A_l come
+// first, :341, so A1 = h_{l-1}, A2 = z).  One launch per layer: the intermediates are a few KB per patch and HBM is
+// idle next to the synthesis kernel, so nothing is gained by keeping them on chip.
+//
+// Precision: tcgen05 kind::f16 has an 11-bit significand.  Every fp32 operand x is split into two fp16 numbers,
+// hi = rn16(x), lo = rn16(x - hi) (22 significant bits), and the product is formed from three MMAs,
+//   A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi        (the dropped lo.lo term is 2^-22 relative),
+// accumulated in fp32 in TMEM: ~1e-6 relative, i.e. the noise level of an fp32 FFMA loop with a different summation
+// order.  tests/test_gpu_parity.py holds the result to 1e-5 against the reference.
+//
+// Per CTA: one 128-row tile, all N columns (N = 64, 128 or 256), K in slabs of 64 through a 2-stage ring.
+//   warps 0-3  A producers: thread = row; load 64 fp32 (one slab ahead, in registers), split, write both halves in
+//              the UMMA K-major core-matrix layout; afterwards the epilogue (tcgen05.ld, bias, activation, store)
+//   warp 4     MMA issuer (converged warp + elect.sync); owns the TMEM allocation
+//   warp 5     weight producer: one cp.async.bulk per slab (hi and lo halves are contiguous in the packed array)
+#include "tc_ptx.cuh"
+
+namespace mrinr {
+namespace dense {
+
+constexpr int kBM = 128;
+constexpr int kSlabK = 64;
+constexpr int kStages = 2;
+constexpr int kThreads = 192;
+constexpr int kAHalfBytes = kBM * kSlabK * 2;          // 16 KB: [8 kc][128 rows][8] fp16
+
+template <int N>
+struct Cfg {
+  static constexpr int kWHalfBytes = N * kSlabK * 2;   // [8 kc][N][8] fp16
+  static constexpr int kStageBytes = 2 * kAHalfBytes + 2 * kWHalfBytes;
+  static constexpr int kOffBar = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kOffBar + 64 + 16;
+  static constexpr int kTmemCols = N < 32 ? 32 : N;
+};
+
+struct DenseParams {
+  const float* a1; long long lda1; int K1;
+  const float* a2; long long lda2; int K2;
+  const uint16_t* w;      // packed by pack_split_kernel
+  const float* bias;      // [N] or null
+  float* c; long long ldc;
+  long long M;
+  int act;                // 0 none, 1 relu, 2 leaky relu
+  float slope;
+  int32_t* errflag;
+};
+
+// W [N, K] fp32 row-major (nn.Linear / flattened Conv2d weight) -> [K/64 slabs][hi, lo][8 kc][N][8] fp16
+__global__ void pack_split_kernel(const float* __restrict__ w, int N, int K, uint16_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * K) return;
+  const int e = (int)(i & 7);
+  const int n = (int)((i >> 3) % N);
+  const int kc = (int)(((i >> 3) / N) & 7);
+  const int slab = (int)((i >> 3) / N) >> 3;
+  const float x = w[(long long)n * K + slab * kSlabK + kc * 8 + e];
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  const long long base = (long long)slab * 2 * 8 * N * 8 + ((long long)kc * N + n) * 8 + e;
+  out[base] = *reinterpret_cast<const uint16_t*>(&hi);
+  out[base + (long long)8 * N * 8] = *reinterpret_cast<const uint16_t*>(&lo);
+}
+
+__device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& hi, uint4& lo) {
+  const float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int N>
+__global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DenseParams P) {
+  using C = Cfg<N>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kOffBar + 64);
+  const uint32_t bar0 = smem_u32(s_bar);
+  // barriers: a_full[2] (4 producer warps), w_full[2] (tx), empty[2] (commit), acc_full
+  auto bar_afull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto bar_wfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (uint32_t)(4 + s); };
+  const uint32_t bar_acc = bar0 + 8u * 6u;
+  const int n_slabs = (P.K1 + P.K2) / kSlabK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_afull(s), 4);
+      mbar_init(bar_wfull(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp < 4) {
+    // =========================== A producers, then epilogue ===========================
+    const long long row = (long long)blockIdx.x * kBM + tid;
+    const bool live = row < P.M;
+    auto load_slab = [&](int slab, float4 (&r)[16]) {
+      const int k = slab * kSlabK;
+      const float* src = (k < P.K1) ? P.a1 + row * P.lda1 + k : P.a2 + row * P.lda2 + (k - P.K1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = live ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 r[16];
+    if (n_slabs > 0) load_slab(0, r);
+    for (int slab = 0; slab < n_slabs; ++slab) {
+      const int st = slab % kStages;
+      mbar_wait(bar_empty(st), ((slab / kStages) & 1u) ^ 1u, P.errflag, 21);
+      uint8_t* a_hi = smem + st * C::kStageBytes;
+      uint8_t* a_lo = a_hi + kAHalfBytes;
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        uint4 hi, lo;
+        split8(r[2 * kc], r[2 * kc + 1], hi, lo);
+        *reinterpret_cast<uint4*>(a_hi + kc * (kBM * 16) + tid * 16) = hi;
+        *reinterpret_cast<uint4*>(a_lo + kc * (kBM * 16) + tid * 16) = lo;
+      }
+      if (slab + 1 < n_slabs) load_slab(slab + 1, r);      // in flight while the tensor core works on this slab
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_afull(st));
+    }
+    // ---- epilogue: this thread owns row `row` (TMEM lane 32*warp + lane) ----
+    mbar_wait(bar_acc, 0u, P.errflag, 22);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float* crow = P.c + row * P.ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      tmem_ld_wait();
+      float y[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = __uint_as_float(v[i]);
+        if (P.bias) x += __ldg(P.bias + c0 + i);
+        if (P.act == 1) x = fmaxf(x, 0.f);
+        else if (P.act == 2) x = x > 0.f ? x : x * P.slope;
+        y[i] = x;
+      }
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(crow + c0 + 4 * i) = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = make_idesc(0, kBM, N);
+    for (int slab = 0; slab < n_slabs; ++slab) {
+      const int st = slab % kStages;
+      const uint32_t par = (slab / kStages) & 1u;
+      mbar_wait_backoff(bar_afull(st), par, P.errflag, 23, 32);
+      mbar_wait_backoff(bar_wfull(st), par, P.errflag, 24, 32);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + st * C::kStageBytes);
+        const uint64_t a_hi = make_smem_desc(sa, kBM * 16, 128);
+        const uint64_t a_lo = make_smem_desc(sa + kAHalfBytes, kBM * 16, 128);
+        const uint64_t b_hi = make_smem_desc(sa + 2 * kAHalfBytes, N * 16, 128);
+        const uint64_t b_lo = make_smem_desc(sa + 2 * kAHalfBytes + C::kWHalfBytes, N * 16, 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = (uint64_t)((k * 2 * kBM * 16) >> 4);
+          const uint64_t db = (uint64_t)((k * 2 * N * 16) >> 4);
+          // small terms first
+          umma_f16(tmem_base, a_lo + da, b_hi + db, idesc, (slab | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, a_hi + da, b_lo + db, idesc, 1u);
+          umma_f16(tmem_base, a_hi + da, b_hi + db, idesc, 1u);
+        }
+        umma_commit(bar_empty(st));
+        if (slab == n_slabs - 1) umma_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      for (int slab = 0; slab < n_slabs; ++slab) {
+        const int st = slab % kStages;
+        mbar_wait_backoff(bar_empty(st), ((slab / kStages) & 1u) ^ 1u, P.errflag, 25);
+        mbar_expect_tx(bar_wfull(st), 2u * C::kWHalfBytes);
+        bulk_g2s(smem_u32(smem + st * C::kStageBytes + 2 * kAHalfBytes),
+                 reinterpret_cast<const uint8_t*>(P.w) + (size_t)slab * 2 * C::kWHalfBytes, 2u * C::kWHalfBytes,
+                 bar_wfull(st));
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int N>
+static int launch_n(const DenseParams& P, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    MRINR_CUDA(cudaFuncSetAttribute(dense_split_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<N>::kSmemBytes));
+    configured = true;
+  }
+  const long long grid = (P.M + kBM - 1) / kBM;
+  dense_split_kernel<N><<<(unsigned)grid, kThreads, Cfg<N>::kSmemBytes, st>>>(P);
+  count_launch();
+  return check_launch("dense_split");
+}
+
+}  // namespace dense
+
+bool dense_split_supported(int N, int K1, int K2) {
+  return (N == 64 || N == 128 || N == 256) && K1 > 0 && K1 % dense::kSlabK == 0 && K2 >= 0 && K2 % dense::kSlabK == 0;
+}
+
+int run_pack_split(const float* w, int N, int K, uint16_t* out, cudaStream_t st) {
+  const long long n = (long long)N * K;
+  dense::pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, N, K, out);
+  count_launch();
+  return check_launch("pack_split");
+}
+
+// act: 0 none, 1 relu, 2 leaky relu (slope)
+int launch_dense_split(const float* a1, long long lda1, int K1, const float* a2, long long lda2, int K2,
+                       const uint16_t* w_packed, const float* bias, int N, int act, float slope, float* c,
+                       long long ldc, long long M, int32_t* errflag, cudaStream_t st) {
+  MRINR_REQUIRE(dense_split_supported(N, K1, K2), MRINR_E_UNSUPPORTED,
+                "dense_split: unsupported shape (N=%d K1=%d K2=%d): N in {64,128,256}, K multiples of 64", N, K1, K2);
+  MRINR_REQUIRE(aligned16(a1) && (K2 == 0 || aligned16(a2)) && aligned16(c) && lda1 % 4 == 0 && lda2 % 4 == 0 &&
+                    ldc % 4 == 0,
+                MRINR_E_ALIGN, "dense_split: operands must be 16-byte aligned with row strides that are multiples of 4");
+  if (M <= 0) return 0;
+  dense::DenseParams P;
+  P.a1 = a1; P.lda1 = lda1; P.K1 = K1; P.a2 = a2; P.lda2 = lda2; P.K2 = K2; P.w = w_packed; P.bias = bias;
+  P.c = c; P.ldc = ldc; P.M = M; P.act = act; P.slope = slope; P.errflag = errflag;
+  if (N == 64) return dense::launch_n<64>(P, st);
+  if (N == 128) return dense::launch_n<128>(P, st);
+  return dense::launch_n<256>(P, st);
+}
+
+}  // namespace mrinr

@@ -6,12 +6,14 @@ same ``state_dict`` layout (31 tensors: ``grid``, ``net.layers.{i}.{weight,bias}
 ``forward(tiles [B,32,32]) -> [B,S,S]`` (modulated_siren.py:435-457) -- but the forward is inference only
 and runs on the hand-written sm_100a kernels of ``libmrinr.so``:
 
-* modulator: one launch for all layers (``mrinr_modulator_forward``),
+* patch encoder: two fused strided convolutions (fp32 FFMA) + the 8x8 convolution and the linear layer as
+  split-fp16 tcgen05 products (``mrinr_encoder_forward``),
+* modulator: one split-fp16 tcgen05 launch per layer (``mrinr_modulator_forward``; fp32 FFMA in "fp32" mode),
 * synthesis net over the coordinate grid of every patch: one persistent tcgen05 kernel
   (``mrinr_siren_forward``); the coordinates are the module's ``grid`` buffer, as in the reference (:448).
 
-The patch encoder (3 convolutions + 1 linear, 0.3 % of the FLOPs) stays a PyTorch/cuDNN submodule
-(SURVEY.md section 8f #1).  There is no CPU path: CPU tensors raise.
+``MRINR_ENCODER=cudnn`` routes the patch encoder through its PyTorch/cuDNN submodule instead (A/B aid).
+There is no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
@@ -142,11 +144,25 @@ class Encoder(nn.Module):
                 "(the VGG ablation encoder is out of scope, SURVEY.md section 2)")
         self.encoder = FixedEncoder(encoder_path, device, latent_dim)
         self.fc = nn.Identity()
+        self._owner = None  # set by ModulatedSiren (weak reference)
 
-    def forward(self, x):
+    def params(self):
+        """conv1 w,b, conv2 w,b, conv3 w,b, fc w,b (siren_encoder.py:503-512: Sequential indices 0, 2, 4, 7)."""
+        seq = self.encoder.encoder
+        return [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[4].weight, seq[4].bias,
+                seq[7].weight, seq[7].bias]
+
+    def forward_torch(self, x):
+        """The same layers through PyTorch (cuDNN on a GPU): an A/B and debugging aid, not the product path."""
         # fp32 like the reference's eval path (no TF32: the CPU reference is plain fp32)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             return self.fc(self.encoder(x))
+
+    def forward(self, x, workspace=None):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None or os.environ.get("MRINR_ENCODER", "") == "cudnn" or tuple(x.shape[1:]) != (32, 32):
+            return self.forward_torch(x)
+        return ops.encoder_forward(owner._packed(), x.to(torch.float32).contiguous(), workspace=workspace)
 
 
 class ModulatedSiren(nn.Module):
@@ -176,6 +192,7 @@ class ModulatedSiren(nn.Module):
         import weakref
 
         self.modulator._owner = weakref.ref(self)
+        self.encoder._owner = weakref.ref(self)
         self._pack_key = None
         self._pack = None
 
@@ -187,6 +204,7 @@ class ModulatedSiren(nn.Module):
         ts += [self.net.last_layer.weight, self.net.last_layer.bias]
         for seq in self.modulator.layers:
             ts += [seq[0].weight, seq[0].bias]
+        ts += self.encoder.params()
         return ts
 
     def _packed(self) -> ops.PackedWeights:
@@ -207,9 +225,15 @@ class ModulatedSiren(nn.Module):
                 mod_weights=[s[0].weight for s in self.modulator.layers],
                 mod_biases=[s[0].bias for s in self.modulator.layers],
                 w0=self.net.w0, w0_initial=self.net.w0_initial, activation=self.activation,
-                precision=self.precision, siren_patch_size=self.siren_patch_size)
+                precision=self.precision, siren_patch_size=self.siren_patch_size,
+                encoder_params=self.encoder.params() if self._encoder_kernel_ok() else None,
+                outer_patch_size=self.outer_patch_size)
             self._pack_key = key
         return self._pack
+
+    def _encoder_kernel_ok(self) -> bool:
+        # the reference's custom encoder is hard-wired to 32x32 patches and a 64 -> latent_dim linear layer
+        return self.outer_patch_size == 32 and self.latent_dim in (64, 128, 256)
 
     def _check_inference(self) -> None:
         if self.training and self.dropout > 0:
@@ -220,10 +244,11 @@ class ModulatedSiren(nn.Module):
                                "test_mod_siren.py:131-132 does")
 
     # ---- the two halves of forward, exposed for the batched pipeline
-    def modulations(self, tiles: torch.Tensor) -> torch.Tensor:
+    def modulations(self, tiles: torch.Tensor, out: Optional[torch.Tensor] = None,
+                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``self.modulator(self.encoder(tiles))`` (modulated_siren.py:446) -> ``[L,B,H]``."""
-        z = self.encoder(tiles)
-        return ops.modulator_forward(self._packed(), z.contiguous())
+        z = self.encoder(tiles, workspace=workspace)
+        return ops.modulator_forward(self._packed(), z.contiguous(), out=out)
 
     def synthesize(self, mods: torch.Tensor, black: Optional[torch.Tensor] = None,
                    out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -34,7 +34,8 @@ class PackedWeights:
                  net_biases: Sequence[Optional[torch.Tensor]], last_weight: torch.Tensor,
                  last_bias: Optional[torch.Tensor], mod_weights: Sequence[torch.Tensor],
                  mod_biases: Sequence[torch.Tensor], w0: float, w0_initial: float, activation: str,
-                 precision: str, siren_patch_size: int):
+                 precision: str, siren_patch_size: int,
+                 encoder_params: Optional[Sequence[torch.Tensor]] = None, outer_patch_size: int = 32):
         lib = _lib.load()
         if activation not in _lib.ACTIVATIONS:
             # the reference treats anything but "morlet" as sine (modulated_siren.py:120-123)
@@ -84,6 +85,20 @@ class PackedWeights:
         view.d_mod_bias = ctypes.cast(mb, ctypes.POINTER(c_void_p))
         view.d_last_weight = f32(last_weight, "net.last_layer.weight").data_ptr()
         view.d_last_bias = None if last_bias is None else f32(last_bias, "net.last_layer.bias").data_ptr()
+        # patch encoder (optional): conv1 w,b, conv2 w,b, conv3 w,b, fc w,b  (siren_encoder.py:503-512)
+        view.outer_patch_size = int(outer_patch_size)
+        self.has_encoder = encoder_params is not None
+        if encoder_params is not None:
+            names = ("conv1_weight", "conv1_bias", "conv2_weight", "conv2_bias", "conv3_weight", "conv3_bias",
+                     "fc_weight", "fc_bias")
+            shapes = ((16, 1, 3, 3), (16,), (32, 16, 3, 3), (32,), (64, 32, 8, 8), (64,), (view.latent_dim, 64),
+                      (view.latent_dim,))
+            if len(encoder_params) != 8:
+                raise RuntimeError("encoder_params must hold 8 tensors (3 convolutions + 1 linear, weight and bias)")
+            for n, shp, t in zip(names, shapes, encoder_params):
+                if tuple(t.shape) != shp:
+                    raise RuntimeError(f"encoder {n} has shape {tuple(t.shape)}, expected {shp}")
+                setattr(view, "d_enc_" + n, f32(t, "encoder." + n).data_ptr())
         handle = c_void_p()
         with torch.cuda.device(dev):
             rc = lib.mrinr_pack_weights(ctypes.byref(view), _lib.PRECISIONS[precision], _lib.stream_ptr(dev),
@@ -120,6 +135,39 @@ class PackedWeights:
             _lib.check(_lib.load().mrinr_packed_layer0_table(self.handle, out.data_ptr(), _lib.stream_ptr(self.device)),
                        "packed_layer0_table")
         return out
+
+
+def encoder_forward(packed: PackedWeights, patches: torch.Tensor, out: Optional[torch.Tensor] = None,
+                    workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``Encoder.forward`` (modulated_siren.py:282-301 -> siren_encoder.py:565-577): patches ``[B,32,32]`` ->
+    latent ``[B,Z]``.  ``workspace``: optional uint8 tensor of ``encoder_workspace_bytes(B)`` bytes (reused by the
+    batched pipeline); allocated per call otherwise."""
+    lib = _lib.load()
+    _lib.require_cuda(patches, "patches", torch.float32)
+    if not packed.has_encoder:
+        raise RuntimeError("these PackedWeights were built without encoder parameters")
+    if patches.dim() != 3 or tuple(patches.shape[1:]) != (32, 32) or not patches.is_contiguous():
+        raise RuntimeError(f"patches must be a contiguous [B,32,32] tensor, got {tuple(patches.shape)}")
+    B = patches.shape[0]
+    if out is None:
+        out = torch.empty(B, packed.Z, dtype=torch.float32, device=patches.device)
+    else:
+        _lib.require_cuda(out, "out", torch.float32)
+        assert tuple(out.shape) == (B, packed.Z) and out.is_contiguous()
+    need = encoder_workspace_bytes(B)
+    if workspace is None:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=patches.device)
+    elif workspace.numel() * workspace.element_size() < need:
+        raise RuntimeError(f"encoder workspace too small: {workspace.numel() * workspace.element_size()} < {need}")
+    with torch.cuda.device(patches.device):
+        _lib.check(lib.mrinr_encoder_forward(packed.handle, patches.data_ptr(), B, out.data_ptr(), workspace.data_ptr(),
+                                             workspace.numel() * workspace.element_size(),
+                                             _lib.stream_ptr(patches.device)), "encoder_forward")
+    return out
+
+
+def encoder_workspace_bytes(B: int) -> int:
+    return int(_lib.load().mrinr_encoder_workspace_bytes(B))
 
 
 def modulator_forward(packed: PackedWeights, latent: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -2,7 +2,7 @@
 slices per launch instead of one slice per Python iteration (test_mod_siren.py:196-234).
 
     images [N,H,W]  --image_to_patches + black mask-->  patches [N*P,O,O], black [N*P]
-                    --encoder (cuDNN) + modulator kernel-->  mods [L,N*P,Hd]
+                    --encoder kernels + modulator (split-fp16 tcgen05 products)-->  mods [L,N*P,Hd]
                     --fused tcgen05 synthesis kernel (black patches skipped, zero-filled)-->  [N*P,S,S]
                     --weighted overlap reassembly-->  recon [N, nV*I, nH*I]
 
@@ -63,12 +63,15 @@ class ReconstructionPipeline:
         mods_buf = self._buffer("mods", (packed.L * cs * P * packed.H,), torch.float32, dev)
         tiles_buf = self._buffer("tiles", (cs * P, S, S), torch.float32, dev)
         ws_buf = self._buffer("ws", (int(ops._lib.load().mrinr_siren_workspace_bytes(cs * P)),), torch.uint8, dev)
+        enc_ws = None
+        if packed.has_encoder:
+            enc_ws = self._buffer("enc_ws", (max(16, ops.encoder_workspace_bytes(cs * P)),), torch.uint8, dev)
         for s0 in range(0, N, cs):
             n = min(cs, N - s0)
             B = n * P
             patches, _, black = ops.image_to_patches(images[s0:s0 + n], O, I, with_black_mask=skip_black,
                                                      out=patches_buf[:B])
-            z = m.encoder(patches)
+            z = m.encoder(patches, workspace=enc_ws)
             mods = ops.modulator_forward(packed, z.contiguous(), out=mods_buf[: packed.L * B * packed.H].view(packed.L, B, packed.H))
             if kernel_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -135,6 +135,52 @@ def test_modulator_matches_reference(golden, case):
 
 
 @pytest.mark.parametrize("case", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_modulator_tensor_core_and_ffma_paths(golden, case, precision):
+    """fp16 mode runs the modulator as split-fp16 tcgen05 products (3 MMAs per product), fp32 mode as FFMA:
+    both must meet the same 1e-5 bar against the reference's modulations."""
+    name, sd_kw, act, model_kw = case
+    m, sd = _model(sd_kw, act, model_kw, precision)
+    g = golden["model_forward"]
+    z = torch.from_numpy(g[f"{name}_latent"]).to(DEV)
+    with torch.no_grad():
+        mods = torch.stack(list(m.modulator(z))).cpu().numpy()
+    err = np.abs(mods - g[f"{name}_mods"]).max()
+    print(f"{name} {precision}: modulator max-abs err {err:.3e}")
+    np.testing.assert_allclose(mods, g[f"{name}_mods"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
+def test_encoder_matches_reference(golden, case):
+    """mrinr_encoder_forward (conv kernels + split-fp16 products) against the reference encoder's latents."""
+    name, sd_kw, act, model_kw = case
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    tiles = torch.from_numpy(synth_tiles(100 + sd_kw["seed"], 5)).to(DEV)
+    with torch.no_grad():
+        z = m.encoder(tiles)
+    assert m._packed().has_encoder
+    want = golden["model_forward"][f"{name}_latent"]
+    err = np.abs(z.cpu().numpy() - want).max()
+    print(f"{name}: encoder max-abs err {err:.3e} (|latent| max {np.abs(want).max():.3f})")
+    np.testing.assert_allclose(z.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B", [1, 3, 130, 1027])
+def test_encoder_matches_oracle_ragged_batches(B):
+    """B is not a multiple of the 4-patch convolution pass nor of the 128-row product tile."""
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    tiles_np = synth_tiles(500 + B, B)
+    with torch.no_grad():
+        z = m.encoder(torch.from_numpy(tiles_np).to(DEV)).cpu().numpy()
+        z_mods = torch.stack(list(m.modulator(torch.from_numpy(z).to(DEV)))).cpu().numpy()
+    want = osiren.encoder_forward(sd, torch.from_numpy(tiles_np))
+    np.testing.assert_allclose(z, want.numpy(), rtol=1e-5, atol=1e-5)
+    want_mods = torch.stack(osiren.modulator_forward(sd, want, 5)).numpy()
+    np.testing.assert_allclose(z_mods, want_mods, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
 def test_layer0_table(case):
     name, sd_kw, act, model_kw = case
     m, sd = _model(sd_kw, act, model_kw, "fp32")

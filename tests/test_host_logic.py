@@ -111,11 +111,15 @@ def test_fixed_encoder_loads_reference_checkpoint_format():
         torch.save({"state_dict": ckpt}, path)
         m = make(encoder_path=path)
     assert torch.equal(m.encoder.encoder.encoder[7].weight, sd[p + "7.weight"])
-    # the encoder forward (PyTorch submodule) equals the oracle restatement
+    # the loaded layers (evaluated through PyTorch, the A/B aid) equal the oracle restatement ...
     tiles = torch.rand(3, 32, 32)
     with torch.no_grad():
-        z = m.encoder(tiles)
+        z = m.encoder.forward_torch(tiles)
     assert torch.allclose(z, osiren.encoder_forward(sd, tiles), atol=1e-6)
+    # ... and the product path refuses CPU tensors instead of falling back
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            m.encoder(tiles)
 
 
 def test_shard_range_partitions_every_item_once():

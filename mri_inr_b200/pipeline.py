@@ -37,6 +37,45 @@ class ReconstructionPipeline:
             self._buf[key] = t
         return t[:numel].view(*shape)
 
+    def _prepare(self, H: int, W: int, n_max: int, dev):
+        """Chunk-sized, reusable intermediates for images of H x W (allocated once per shape)."""
+        m = self.model
+        O, I, S = m.outer_patch_size, m.inner_patch_size, m.siren_patch_size
+        nV, nH = -(-H // I), -(-W // I)
+        P = nV * nH
+        packed = m._packed()
+        cs = max(1, min(self.chunk_slices, n_max))
+        bufs = dict(
+            patches=self._buffer("patches", (cs * P, O, O), torch.float32, dev),
+            mods=self._buffer("mods", (packed.L * cs * P * packed.H,), torch.float32, dev),
+            tiles=self._buffer("tiles", (cs * P, S, S), torch.float32, dev),
+            ws=self._buffer("ws", (int(ops._lib.load().mrinr_siren_workspace_bytes(cs * P)),), torch.uint8, dev),
+            enc_ws=(self._buffer("enc_ws", (max(16, ops.encoder_workspace_bytes(cs * P)),), torch.uint8, dev)
+                    if packed.has_encoder else None),
+            wts=_weights_on(S, dev),
+        )
+        return packed, cs, (nV, nH, P, O, I, S), bufs
+
+    def _chunk(self, images: torch.Tensor, out: torch.Tensor, packed, geom, bufs, skip_black: bool,
+               kernel_events: Optional[list]) -> None:
+        """One chunk of slices, a handful of launches on the current stream: images [n,H,W] -> out [n,nV*I,nH*I]."""
+        m = self.model
+        nV, nH, P, O, I, S = geom
+        n = images.shape[0]
+        B = n * P
+        patches, _, black = ops.image_to_patches(images, O, I, with_black_mask=skip_black, out=bufs["patches"][:B])
+        z = m.encoder(patches, workspace=bufs["enc_ws"])
+        mods = ops.modulator_forward(packed, z.contiguous(),
+                                     out=bufs["mods"][: packed.L * B * packed.H].view(packed.L, B, packed.H))
+        if kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        tiles = ops.siren_forward(packed, mods, black=black, out=bufs["tiles"][:B], workspace=bufs["ws"])
+        if kernel_events is not None:
+            e1.record()
+            kernel_events.append((e0, e1, B))
+        ops.patches_to_image(tiles.view(B, S, S), n, (nV, nH), I, weights=bufs["wts"], black=black, out=out)
+
     @torch.no_grad()
     def reconstruct(self, images: torch.Tensor, out: Optional[torch.Tensor] = None,
                     skip_black: bool = True, kernel_events: Optional[list] = None) -> torch.Tensor:
@@ -50,35 +89,75 @@ class ReconstructionPipeline:
             raise RuntimeError("images must be a CUDA tensor [N,H,W]")
         images = images.to(torch.float32).contiguous()
         N, H, W = images.shape
-        O, I, S = m.outer_patch_size, m.inner_patch_size, m.siren_patch_size
-        nV, nH = -(-H // I), -(-W // I)
-        P = nV * nH
         dev = images.device
+        packed, cs, geom, bufs = self._prepare(H, W, N, dev)
+        nV, nH, P, O, I, S = geom
         if out is None:
             out = torch.empty(N, nV * I, nH * I, dtype=torch.float32, device=dev)
-        packed = m._packed()
-        wts = _weights_on(S, dev)
-        cs = max(1, min(self.chunk_slices, N))
-        patches_buf = self._buffer("patches", (cs * P, O, O), torch.float32, dev)
-        mods_buf = self._buffer("mods", (packed.L * cs * P * packed.H,), torch.float32, dev)
-        tiles_buf = self._buffer("tiles", (cs * P, S, S), torch.float32, dev)
-        ws_buf = self._buffer("ws", (int(ops._lib.load().mrinr_siren_workspace_bytes(cs * P)),), torch.uint8, dev)
-        enc_ws = None
-        if packed.has_encoder:
-            enc_ws = self._buffer("enc_ws", (max(16, ops.encoder_workspace_bytes(cs * P)),), torch.uint8, dev)
         for s0 in range(0, N, cs):
             n = min(cs, N - s0)
-            B = n * P
-            patches, _, black = ops.image_to_patches(images[s0:s0 + n], O, I, with_black_mask=skip_black,
-                                                     out=patches_buf[:B])
-            z = m.encoder(patches, workspace=enc_ws)
-            mods = ops.modulator_forward(packed, z.contiguous(), out=mods_buf[: packed.L * B * packed.H].view(packed.L, B, packed.H))
-            if kernel_events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            tiles = ops.siren_forward(packed, mods, black=black, out=tiles_buf[:B], workspace=ws_buf)
-            if kernel_events is not None:
-                e1.record()
-                kernel_events.append((e0, e1, B))
-            ops.patches_to_image(tiles.view(B, S, S), n, (nV, nH), I, weights=wts, black=black, out=out[s0:s0 + n])
+            self._chunk(images[s0:s0 + n], out[s0:s0 + n], packed, geom, bufs, skip_black, kernel_events)
         return out
+
+    @torch.no_grad()
+    def reconstruct_from_host(self, host_images: torch.Tensor, host_out: Optional[torch.Tensor] = None,
+                              device_out: Optional[torch.Tensor] = None, device=None,
+                              skip_black: bool = True) -> torch.Tensor:
+        """The same reconstruction for slices that live in (pinned) HOST memory: ``host_images [N,H,W]`` ->
+        ``host_out [N, nV*I, nH*I]`` (pinned host) or, if ``device_out`` is given instead, a device tensor (the
+        multi-GPU sweep gathers on the device first).
+
+        Chunks are double-buffered over three streams -- upload of chunk i+1, compute of chunk i and download of
+        chunk i-1 run concurrently (PCIe is full duplex and the copy engines are independent of the SMs) -- so the
+        transfers cost one chunk of latency instead of two full passes.  On return all work has been enqueued and
+        the CURRENT stream waits for it: synchronise that stream (or the device) before reading ``host_out``."""
+        m = self.model
+        m._check_inference()
+        if host_images.dim() != 3 or host_images.is_cuda or host_images.dtype != torch.float32:
+            raise RuntimeError("host_images must be a CPU fp32 tensor [N,H,W] (pinned for asynchronous copies)")
+        if device is None:
+            device = m.grid.device
+        dev = torch.device(device)
+        N, H, W = host_images.shape
+        packed, cs, geom, bufs = self._prepare(H, W, N, dev)
+        nV, nH, P, O, I, S = geom
+        if device_out is None and host_out is None:
+            host_out = torch.empty(N, nV * I, nH * I, dtype=torch.float32).pin_memory()
+        comp = torch.cuda.current_stream(dev)
+        if "streams" not in self._buf:
+            self._buf["streams"] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._buf["streams"]
+        in_buf = [self._buffer(f"h2d{i}", (cs, H, W), torch.float32, dev) for i in range(2)]
+        out_buf = [self._buffer(f"d2h{i}", (cs, nV * I, nH * I), torch.float32, dev) for i in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_comp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        start = torch.cuda.Event()
+        start.record(comp)
+        s_in.wait_event(start)          # nothing of this call may overtake earlier work on the caller's stream
+        s_out.wait_event(start)
+        for i, s0 in enumerate(range(0, N, cs)):
+            n = min(cs, N - s0)
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_comp[k])                 # chunk i-2 no longer reads in_buf[k]
+                in_buf[k][:n].copy_(host_images[s0:s0 + n], non_blocking=True)
+                ev_in[k].record(s_in)
+            comp.wait_event(ev_in[k])
+            if device_out is not None:
+                self._chunk(in_buf[k][:n], device_out[s0:s0 + n], packed, geom, bufs, skip_black, None)
+                ev_comp[k].record(comp)
+            else:
+                if i >= 2:
+                    comp.wait_event(ev_out[k])                  # chunk i-2 has left out_buf[k]
+                self._chunk(in_buf[k][:n], out_buf[k][:n], packed, geom, bufs, skip_black, None)
+                ev_comp[k].record(comp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_comp[k])
+                    host_out[s0:s0 + n].copy_(out_buf[k][:n], non_blocking=True)
+                    ev_out[k].record(s_out)
+        done = torch.cuda.Event()
+        done.record(s_out)
+        comp.wait_event(done)
+        return device_out if device_out is not None else host_out

@@ -289,6 +289,27 @@ def test_pipeline_matches_reference_flow():
         assert np.abs(rec[i] - want).max() <= 1e-3
 
 
+def test_host_pipeline_equals_device_pipeline():
+    """reconstruct_from_host (double-buffered upload / compute / download over three streams) must return exactly
+    what reconstruct returns for device-resident slices -- with more chunks than buffers and a ragged last chunk."""
+    from mri_inr_b200.pipeline import ReconstructionPipeline
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    imgs = torch.from_numpy(np.stack([synth_image(70 + i, 64, 80) for i in range(7)]))
+    pipe = ReconstructionPipeline(m, chunk_slices=2)
+    want = pipe.reconstruct(imgs.to(DEV)).cpu()
+    host_in = imgs.pin_memory()
+    for _ in range(2):                                  # second call reuses the buffers and streams
+        got = pipe.reconstruct_from_host(host_in)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    dev_out = torch.empty(7, 64, 80, device=DEV)
+    pipe.reconstruct_from_host(host_in, device_out=dev_out)
+    torch.cuda.synchronize()
+    assert torch.equal(dev_out.cpu(), want)
+
+
 def test_cpu_tensors_and_grad_are_refused():
     name, sd_kw, act, model_kw = MODEL_CASES[0]
     m, sd = _model(sd_kw, act, model_kw, "fp16")

@@ -15,7 +15,8 @@
 //     1, ...  So a thread (one tile row, 128 or 64 columns) sees the same coordinate for hundreds of consecutive tiles and keeps
 //     its slice of the pre-computed layer-0 table act_0(W_0 g_c + b_0) (MrinrPacked::d_table0) in REGISTERS as packed
 //     16-bit pairs.  The layer-0 phase is then: unpack, multiply by the modulation, pack, store -- no sine.
-//     The table is re-read from global memory only when the block changes (C/128 + 1 times per launch).
+//     The table is re-read from global memory only when the block changes (C/128 + 1 times per sub-block of 128
+//     patches).
 //   * A tile belongs to one patch, so its modulation vectors are warp-uniform.  The producer thread streams them into
 //     a small shared-memory ring with cp.async.bulk (1 KB per patch and layer) and the epilogue reads them with
 //     broadcast LDS.128 -- no per-row global loads, no L1 misses on the critical path (v4: 19 % long-scoreboard stalls).
@@ -99,31 +100,49 @@ __device__ int g_timeline_n;
 #endif
 
 // The schedule of one cluster; every role derives it from the same inputs, so nothing is communicated.
+// The cluster's patches are walked in sub-blocks of kSubBlock patches, block-major inside a sub-block: the modulation
+// vectors of a sub-block (5 KB per patch, read once per coordinate block) then stay in L2 between their
+// C/128 + 1 uses (74 clusters x 128 patches x 5 KB = 47 MB) instead of streaming from HBM every time.
+constexpr int kSubBlock = 128;
 struct Sched {
-  long long pa, np;      // this cluster's patches: compacted indices [pa, pa + np)
+  long long pa;          // this cluster's patches: compacted indices [pa, pa + np)
+  int np;
   int n_full, rem, ksub; // C = 128 n_full + rem; ksub = patches per remainder tile (0 if rem == 0)
-  long long it_full;     // cluster iterations (4 tiles each) per full coordinate block
-  long long it_rem;      // cluster iterations of the remainder block
-  long long total;
+  int n_types;           // coordinate blocks per patch: n_full (+ 1 if rem)
+  long long total;       // cluster iterations (4 tiles each)
 };
+__device__ __forceinline__ int iters_rem(const Sched& s, int n) {   // remainder-block iterations for n patches
+  return s.rem ? ((n + s.ksub - 1) / s.ksub + 3) / 4 : 0;
+}
 __device__ __forceinline__ Sched make_sched(long long n_act, int C, long long cluster_id, long long n_clusters) {
   Sched s;
   s.pa = n_act * cluster_id / n_clusters;
-  s.np = n_act * (cluster_id + 1) / n_clusters - s.pa;
+  s.np = (int)(n_act * (cluster_id + 1) / n_clusters - s.pa);
   s.n_full = C / kTileM;
   s.rem = C - s.n_full * kTileM;
   s.ksub = s.rem ? (kTileM / s.rem < kMaxSub ? kTileM / s.rem : kMaxSub) : 0;
-  s.it_full = (s.np + 3) / 4;
-  const long long rem_tiles = s.rem ? (s.np + s.ksub - 1) / s.ksub : 0;
-  s.it_rem = (rem_tiles + 3) / 4;
-  s.total = s.n_full * s.it_full + s.it_rem;
+  s.n_types = s.n_full + (s.rem ? 1 : 0);
+  const int blocks = s.np / kSubBlock, tail = s.np - blocks * kSubBlock;
+  s.total = (long long)blocks * (s.n_full * (kSubBlock / 4) + iters_rem(s, kSubBlock));
+  if (tail) s.total += s.n_full * ((tail + 3) / 4) + iters_rem(s, tail);
   return s;
 }
-struct Walk {          // (coordinate block, iteration within the block), advanced without divisions
+struct Walk {          // (sub-block, coordinate block, iteration within the block), advanced without divisions
   int type = 0;
-  long long j = 0;
+  int j = 0;
+  int base = 0;        // first patch of the sub-block, relative to Sched::pa
+  int nps = 0;         // patches in the sub-block
+  int itf = 0, itr = 0;
+  __device__ __forceinline__ void set_block(const Sched& s) {
+    nps = s.np - base < kSubBlock ? s.np - base : kSubBlock;
+    itf = (nps + 3) / 4;
+    itr = iters_rem(s, nps);
+  }
   __device__ __forceinline__ void next(const Sched& s) {
-    if (++j == (type < s.n_full ? s.it_full : s.it_rem)) { j = 0; ++type; }
+    if (++j == (type < s.n_full ? itf : itr)) {
+      j = 0;
+      if (++type == s.n_types) { type = 0; base += kSubBlock; set_block(s); }
+    }
   }
 };
 
@@ -349,6 +368,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     };
 
     Walk w;
+    w.set_block(S);
     for (long long it = 0; it <= S.total; ++it) {
       const bool last = (it == S.total);                           // extra pass: only the pending output phases
       const uint32_t use0 = (uint32_t)it * (uint32_t)L;           // modulation-ring sequence number of layer 0
@@ -383,11 +403,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         if (last) continue;
         {
           // which patch does this row belong to?  (a phantom tile / padding row has no output)
-          const long long ti = w.j * 4 + slot * 2 + (long long)rank;
-          const long long pl = cur_type < S.n_full ? ti : ti * S.ksub + sub_row;
+          const int ti = w.j * 4 + slot * 2 + (int)rank;
+          const int pl = cur_type < S.n_full ? ti : ti * S.ksub + sub_row;
           float* o = nullptr;
-          if (row_live && pl < S.np) {
-            const long long patch = P.idx ? (long long)P.idx[S.pa + pl] : S.pa + pl;
+          if (row_live && pl < w.nps) {
+            const long long patch = P.idx ? (long long)P.idx[S.pa + w.base + pl] : S.pa + w.base + pl;
             o = P.out + patch * C + c_row;
           }
           if (slot) out1 = o; else out0 = o;
@@ -527,18 +547,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     if (lane == 0) {
       uint32_t ev = 0;
       Walk w;
+      w.set_block(S);
       for (long long it = 0; it < S.total; ++it, w.next(S)) {
         const bool full = w.type < S.n_full;
         const int nsub = full ? 1 : S.ksub;
         long long patch[2][kMaxSub];
 #pragma unroll
         for (int slot = 0; slot < 2; ++slot) {
-          const long long ti = w.j * 4 + slot * 2 + (long long)rank;
+          const int ti = w.j * 4 + slot * 2 + (int)rank;
 #pragma unroll
           for (int s = 0; s < kMaxSub; ++s) {
-            long long pl = full ? ti : ti * S.ksub + s;
-            if (pl >= S.np) pl = S.np - 1;                       // phantom tile / missing patch: any valid vector
-            patch[slot][s] = P.idx ? (long long)P.idx[S.pa + pl] : S.pa + pl;
+            int pl = full ? ti : ti * S.ksub + s;
+            if (pl >= w.nps) pl = w.nps - 1;                     // phantom tile / missing patch: any valid vector
+            patch[slot][s] = P.idx ? (long long)P.idx[S.pa + w.base + pl] : S.pa + w.base + pl;
           }
         }
         auto issue_mods = [&](int l) {

@@ -10,8 +10,10 @@ batched inference over a synthetic 940-volume-shaped validation set = 940 volume
 set is block-partitioned by slice over the ranks (strong scaling) and the reconstructed slices are gathered to
 rank 0 with point-to-point NCCL transfers inside the timed region.
 
-`value`: slices/s with the inputs resident in HBM.  `e2e`: the same pass through the public pipeline from pinned
-HOST buffers (H2D of the undersampled slices and D2H of the reconstructions inside the timed region).
+`value`: slices/s with the inputs resident in HBM.  `e2e`: the same pass through the public host-buffer API
+(`ReconstructionPipeline.reconstruct_from_host`): pinned HOST slices in, HOST reconstructions out, with the uploads
+and downloads double-buffered against the compute inside the timed region (N > 1: every rank streams its block over
+its own PCIe link into one shared, page-locked host buffer).
 `roofline`: the fused tcgen05 synthesis kernel, timed with CUDA events around every launch in the timed region.
 `cpu_baseline` / `--impl reference`: the reference's own CPU op sequence (oracle/flow.py; the reference is pure
 Python and /root/reference does not exist on the GPU box, so the port is timed: kind "port").
@@ -37,9 +39,10 @@ PATCHES_PER_SLICE, COORDS_PER_PATCH = 400, 576
 FLOP_PER_COORD = 4 * 2 * 256 * 256                       # tensor-eligible hidden contractions
 METRIC = "reconstructed 320x320 slices/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of the synthesis kernel from the ncu --set full capture in
-# profiles/r01_ncu_siren_v4b.txt (132.14 MB + 40.16 MB for 64 slices); algorithmic: 400 x 5 KB of modulations read +
-# 400 x 2304 B of outputs written per slice = 2.97 MB
-DRAM_TRAFFIC_BYTES_PER_SLICE = (132.137216e6 + 40.158976e6) / 64
+# profiles/r01_ncu_siren_v5.txt (136.77 MB + 40.91 MB for 64 slices, the v5 kernel with sub-block walking);
+# algorithmic: 400 x 5 KB of modulations read + 400 x 2304 B of outputs written per slice = 2.97 MB (part of the
+# output is still in L2 when the kernel ends)
+DRAM_TRAFFIC_BYTES_PER_SLICE = (136.77e6 + 40.91e6) / 64
 MODEL_KW = dict(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=1.0, w0_initial=30.0,
                 use_bias=True, dropout=0.1, modulate=True, encoder_type="custom", encoder_path=None,
                 outer_patch_size=32, inner_patch_size=16, siren_patch_size=24)
@@ -191,7 +194,13 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the first communicator
+        # is created, so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     n_total = args.slices
@@ -249,18 +258,48 @@ def run_ours(args):
     # ---- end to end: pinned host -> device -> pipeline -> pinned host, every step
     # (every rank uploads its block; the reconstructed set lands in host memory of rank 0)
     host_in = torch.empty(n_local, IMG, IMG, dtype=torch.float32).pin_memory()
-    host_out = torch.empty(n_total if rank == 0 else 1, IMG, IMG, dtype=torch.float32).pin_memory()
     host_in.copy_(images)
+    # Result buffer in host memory.  N = 1: a pinned tensor.  N > 1: ONE buffer in POSIX shared memory that every rank
+    # maps and page-locks, so each rank streams its block host -> device -> host over its own PCIe link (the NCCL
+    # gather belongs to the device-resident metric above; funnelling 4.2 GB through rank 0's link would serialise
+    # the downloads).  If shared memory is too small on the box, fall back to gather + one download on rank 0.
+    shared_out, e2e_mode = None, "pinned"
+    if world > 1:
+        path = f"/dev/shm/mrinr_bench_{os.environ.get('MASTER_PORT', '0')}.bin"
+        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        try:
+            if rank == 0:
+                with open(path, "wb") as f:
+                    f.truncate(n_total * IMG * IMG * 4)
+            dist.barrier()
+            shared_out = torch.from_file(path, shared=True, size=n_total * IMG * IMG, dtype=torch.float32).view(n_total, IMG, IMG)
+            rc = torch.cuda.cudart().cudaHostRegister(shared_out.data_ptr(), shared_out.numel() * 4, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed: {rc}")
+            shared_out[s0:s1].zero_()               # touch my pages
+            ok += 1
+        except Exception as e:                      # noqa: BLE001 - any failure selects the fallback on every rank
+            print(f"[bench] rank {rank}: shared host buffer unavailable ({e}); e2e falls back to gather + download", file=sys.stderr)
+        dist.all_reduce(ok)
+        if int(ok.item()) == world:
+            e2e_mode = "shared host buffer, one PCIe link per rank"
+        else:
+            shared_out, e2e_mode = None, "NCCL gather to rank 0, then one download"
+    host_out = None
+    if shared_out is None:
+        host_out = torch.empty(n_total if rank == 0 else 1, IMG, IMG, dtype=torch.float32).pin_memory()
 
     def e2e_step():
         # public API for host-resident slices: chunked, double-buffered upload / compute / download
-        if world > 1:
+        if world == 1:
+            pipe.reconstruct_from_host(host_in, host_out=host_out, device=dev)
+        elif shared_out is not None:
+            pipe.reconstruct_from_host(host_in, host_out=shared_out[s0:s1], device=dev)
+        else:
             pipe.reconstruct_from_host(host_in, device_out=recon, device=dev)
             gather_slices(recon, n_total, dst=0, out=gathered)
             if rank == 0:
                 host_out.copy_(gathered, non_blocking=True)
-        else:
-            pipe.reconstruct_from_host(host_in, host_out=host_out, device=dev)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step()
@@ -299,12 +338,12 @@ def run_ours(args):
                        "l2": f"inputs larger than L2 ({n_local * IMG * IMG * 4 / 1e6:.0f} MB of slices per rank per step; "
                              f"intermediates {args.chunk * 400 * (1024 + 5 * 256 + 576) * 4 / 1e6:.0f} MB per chunk)"},
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": n_total * IMG * IMG * 4,
-                    "d2h_bytes_per_step": n_total * IMG * IMG * 4, "steps": e2e_steps},
+                    "d2h_bytes_per_step": n_total * IMG * IMG * 4, "steps": e2e_steps, "result": e2e_mode},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None,
                          "traffic": DRAM_TRAFFIC_BYTES_PER_SLICE * kern_patches / PATCHES_PER_SLICE / max(len(events), 1),
-                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_ncu_siren_v4b.txt",
+                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_ncu_siren_v5.txt",
                          "kernel": "siren_tc5_kernel (fused modulated-SIREN MLP, tcgen05 cta_group::2)", "peak_source": f"{peak_src}, sustained bf16",
                          "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
                          "kernel_ms_per_step": kern_ms / args.steps, "kernel_launches_timed": len(events),
@@ -313,8 +352,17 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(f"/dev/shm/mrinr_bench_{os.environ.get('MASTER_PORT', '0')}.bin")
+            except OSError:
+                pass
         dist.destroy_process_group()
 
 

@@ -231,6 +231,53 @@ def test_forward_matches_oracle_ragged_batches(precision, tol, B):
     assert err <= tol
 
 
+@pytest.mark.parametrize("S,B", [(12, 37), (16, 9), (20, 23), (24, 131), (32, 6)])
+def test_forward_other_grid_sizes(S, B):
+    """siren_patch_size^2 = 144 / 256 / 400 / 576 / 1024 coordinates per patch: one full coordinate block + a 16-row
+    remainder (2 patches per remainder tile, 96 padding rows), no remainder at all, 3 blocks + 16, the baseline
+    4 blocks + 64, and 8 full blocks -- with patch counts that leave phantom tiles and half-filled remainder tiles."""
+    from mri_inr_b200.modulated_siren import ModulatedSiren
+
+    sd = osiren.synth_state_dict(31 + S, siren_patch_size=S, mod_bias_shift=0.5)
+    m = ModulatedSiren(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=1.0, w0_initial=30.0,
+                       use_bias=True, dropout=0.1, modulate=True, encoder_type="custom", encoder_path=None,
+                       outer_patch_size=32, inner_patch_size=16, siren_patch_size=S, device=torch.device("cpu"),
+                       activation="sine")
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).eval()
+    tiles_np = synth_tiles(900 + S, B)
+    with torch.no_grad():
+        y = m(torch.from_numpy(tiles_np).to(DEV)).cpu().numpy()
+    want = osiren.model_forward(sd, torch.from_numpy(tiles_np), siren_patch_size=S).numpy()
+    assert y.shape == (B, S, S)
+    err = np.abs(y - want).max()
+    print(f"S={S} B={B}: max-abs err {err:.3e}")
+    assert err <= 1e-3
+
+
+def test_forward_large_batch_spans_sub_blocks():
+    """20 000 patches: every cluster walks two sub-blocks of 128 patches plus a ragged tail (the schedule that keeps
+    a sub-block's modulations in L2); compared patch by patch against the fp32 oracle on a sample."""
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    B = 20011
+    rs = np.random.RandomState(3)
+    base = synth_tiles(4242, 64)
+    idx = rs.randint(0, 64, size=B)
+    scale = rs.uniform(0.2, 1.0, size=B).astype(np.float32)
+    tiles_np = base[idx] * scale[:, None, None]
+    with torch.no_grad():
+        y = m(torch.from_numpy(tiles_np).to(DEV)).cpu().numpy()
+    sample = np.concatenate([np.arange(0, 300), rs.randint(0, B, size=300), np.arange(B - 300, B)])
+    want = osiren.model_forward(sd, torch.from_numpy(tiles_np[sample]), activation=act).numpy()
+    err = np.abs(y[sample] - want).max()
+    print(f"B={B}: max-abs err over {len(sample)} sampled patches {err:.3e}")
+    assert err <= 1e-3
+    # the same patch gives the same pixels wherever it sits in the batch (tile / slot / CTA independence)
+    j = int(np.where((idx == idx[0]) & (scale == scale[0]))[0][-1])
+    assert np.array_equal(y[0], y[j])
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_reduced_latent_residual_shape(precision):
     """BASELINE config 4 (builder-defined): L=9, latent 128.  Oracle-only parity (the reference's

@@ -164,6 +164,16 @@ MRINR_API int mrinr_complex_abs(const float* d_in, int64_t n, float* d_out, void
 MRINR_API int mrinr_minmax_normalize(const float* d_in, int64_t G, int64_t n, float* d_out, float* d_scratch,
                            void* stream);
 
+/* ---- image-quality metrics of the evaluation loop: src/util/error.py:23-84 as called by metrics_error (:256-269) -- */
+/* d_original, d_predicted [N,H,W] -> d_out [N,3] (fp64): PSNR, SSIM, NRMSE per pair with the reference's data range
+ * (max over both images - min over both images).  scikit-image definitions with the defaults error.py uses: SSIM
+ * with a 7x7 uniform window, K1 = .01, K2 = .03, sample covariance, 3-pixel border cropped; NRMSE euclidean.
+ * d_scratch: mrinr_image_metrics_scratch_bytes(N) bytes, 8-byte aligned.  Tolerance vs fp64 scikit-image
+ * arithmetic: 1e-3 dB / 1e-4 / 1e-6 relative (window sums are fp32, as scikit-image's are for fp32 images). */
+MRINR_API int64_t mrinr_image_metrics_scratch_bytes(int64_t N);
+MRINR_API int mrinr_image_metrics(const float* d_original, const float* d_predicted, int64_t N, int32_t H, int32_t W,
+                        double* d_out, void* d_scratch, int64_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "mrinr_siren_workspace_bytes", "mrinr_siren_forward",
     "mrinr_image_to_patches", "mrinr_classify_patches", "mrinr_patches_to_image",
     "mrinr_complex_abs", "mrinr_minmax_normalize",
+    "mrinr_image_metrics_scratch_bytes", "mrinr_image_metrics",
 )
 
 
@@ -89,6 +90,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrinr_patches_to_image.restype = c_int
     lib.mrinr_patches_to_image.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                            c_void_p, c_void_p]
+    lib.mrinr_image_metrics_scratch_bytes.restype = c_int64
+    lib.mrinr_image_metrics_scratch_bytes.argtypes = [c_int64]
+    lib.mrinr_image_metrics.restype = c_int
+    lib.mrinr_image_metrics.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]
     lib.mrinr_complex_abs.restype = c_int
     lib.mrinr_complex_abs.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.mrinr_minmax_normalize.restype = c_int

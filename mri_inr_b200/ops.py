@@ -300,3 +300,30 @@ def minmax_normalize(x: torch.Tensor, groups: int = 1) -> torch.Tensor:
         _lib.check(lib.mrinr_minmax_normalize(x.data_ptr(), groups, n, out.data_ptr(), scratch.data_ptr(),
                                               _lib.stream_ptr(x.device)), "minmax_normalize")
     return out
+
+
+def image_metrics(original: torch.Tensor, predicted: torch.Tensor) -> torch.Tensor:
+    """PSNR / SSIM / NRMSE of N image pairs on the device (src/util/error.py:23-84 as called by metrics_error,
+    :256-269): ``original, predicted [N,H,W]`` (or ``[H,W]``) -> ``[N,3]`` float64 (psnr, ssim, nrmse), with the
+    reference's data range ``max(both) - min(both)`` per pair."""
+    lib = _lib.load()
+    _lib.require_cuda(original, "original", torch.float32)
+    _lib.require_cuda(predicted, "predicted", torch.float32)
+    if original.shape != predicted.shape:
+        raise RuntimeError(f"shape mismatch: {tuple(original.shape)} vs {tuple(predicted.shape)}")
+    if original.dim() == 2:
+        original, predicted = original[None], predicted[None]
+    if original.dim() != 3:
+        raise RuntimeError("expected [N,H,W] or [H,W]")
+    original, predicted = original.contiguous(), predicted.contiguous()
+    N, H, W = original.shape
+    out = torch.empty(N, 3, dtype=torch.float64, device=original.device)
+    if N == 0:
+        return out
+    need = int(lib.mrinr_image_metrics_scratch_bytes(N))
+    scratch = torch.empty((need + 7) // 8, dtype=torch.float64, device=original.device)
+    with torch.cuda.device(original.device):
+        _lib.check(lib.mrinr_image_metrics(original.data_ptr(), predicted.data_ptr(), N, H, W, out.data_ptr(),
+                                           scratch.data_ptr(), scratch.numel() * 8, _lib.stream_ptr(original.device)),
+                   "image_metrics")
+    return out

@@ -161,3 +161,21 @@ class ReconstructionPipeline:
         done.record(s_out)
         comp.wait_event(done)
         return device_out if device_out is not None else host_out
+
+    @torch.no_grad()
+    def evaluate(self, undersampled: torch.Tensor, fully_sampled: torch.Tensor, skip_black: bool = True):
+        """``metrics_error`` (src/util/error.py:200-271) for N slices at once, entirely on the device:
+        reconstruct ``undersampled [N,H,W]`` and score it against ``fully_sampled [N,H,W]``.
+
+        Returns ``(recon [N,nV*I,nH*I], metrics [N,3] float64 = psnr, ssim, nrmse)``.  The reference re-assembles the
+        fully sampled image from its patches with ``patches_to_image`` (:244-249); for patches cut by
+        ``image_to_patches`` that is the identity on the (padded) image, so the image itself is scored -- the image
+        size must be a multiple of the inner patch size (320 = 20 x 16 in every configuration of the reference)."""
+        m = self.model
+        I = m.inner_patch_size
+        if undersampled.shape != fully_sampled.shape:
+            raise RuntimeError("undersampled and fully_sampled must have the same shape")
+        if undersampled.shape[-1] % I or undersampled.shape[-2] % I:
+            raise RuntimeError(f"image size {tuple(undersampled.shape[-2:])} is not a multiple of the inner patch size {I}")
+        recon = self.reconstruct(undersampled, skip_black=skip_black)
+        return recon, ops.image_metrics(fully_sampled.to(torch.float32).contiguous(), recon)

@@ -357,6 +357,34 @@ def test_host_pipeline_equals_device_pipeline():
     assert torch.equal(dev_out.cpu(), want)
 
 
+@pytest.mark.parametrize("hw", [(320, 320), (64, 80), (7, 9), (33, 100)])
+def test_image_metrics_match_oracle(hw):
+    """mrinr_image_metrics against the fp64 restatement of the scikit-image calls in error.py:23-84 (oracle/metrics.py;
+    parity UNPINNED against scikit-image itself, see that module).  Tolerances: 1e-3 dB, 1e-4 SSIM, 1e-6 relative NRMSE."""
+    from mri_inr_b200 import metrics, ops
+    from oracle import metrics as ometrics
+
+    h, w = hw
+    rs = np.random.RandomState(h * 1000 + w)
+    full = np.stack([synth_image(200 + i, h, w) for i in range(4)]) if min(h, w) >= 32 else rs.rand(4, h, w).astype(np.float32)
+    noise = rs.normal(scale=[[[0.01]], [[0.05]], [[0.2]], [[0.001]]], size=full.shape).astype(np.float32)
+    pred = (full + noise).astype(np.float32)
+    pred[2] = pred[2] * 0.5 - 0.1                      # a different range: the data-range rule matters
+    got = ops.image_metrics(torch.from_numpy(full).to(DEV), torch.from_numpy(pred).to(DEV)).cpu().numpy()
+    for i in range(4):
+        want = (ometrics.psnr(full[i], pred[i]), ometrics.ssim(full[i], pred[i]), ometrics.nrmse(full[i], pred[i]))
+        print(f"{hw} pair {i}: got {got[i]}, want {want}")
+        assert abs(got[i, 0] - want[0]) <= 1e-3
+        assert abs(got[i, 1] - want[1]) <= 1e-4
+        assert abs(got[i, 2] - want[2]) <= 1e-6 * max(1.0, abs(want[2]))
+    # the single-image helpers mirror error.py's names
+    a, b = torch.from_numpy(full[1]).to(DEV), torch.from_numpy(pred[1]).to(DEV)
+    assert abs(metrics.calculate_psnr(a, b) - got[1, 0]) < 1e-12
+    assert abs(metrics.calculate_ssim(a, b) - got[1, 1]) < 1e-12
+    assert abs(metrics.calculate_nrmse(a, b) - got[1, 2]) < 1e-12
+    assert abs(metrics.calculate_data_range(a, b) - ometrics.data_range(full[1], pred[1])) < 1e-6
+
+
 def test_cpu_tensors_and_grad_are_refused():
     name, sd_kw, act, model_kw = MODEL_CASES[0]
     m, sd = _model(sd_kw, act, model_kw, "fp16")
@@ -414,6 +442,15 @@ def test_psnr_ssim_within_north_star_tolerance():
         assert abs(metrics.psnr(ref_img, rec[i]) - metrics.psnr(ref_img, want)) <= 0.05
         assert abs(metrics.ssim(ref_img, rec[i]) - metrics.ssim(ref_img, want)) <= 1e-3
         assert abs(metrics.nrmse(ref_img, rec[i]) - metrics.nrmse(ref_img, want)) <= 1e-3
+    # the same acceptance check without leaving the device: pipeline.evaluate = metrics_error for N slices
+    rec_dev, got = ReconstructionPipeline(m).evaluate(under, full)
+    got = got.cpu().numpy()
+    for i in range(2):
+        want = flow.reconstruct_slice(sd, under[i].cpu(), activation=act).numpy()
+        ref_img = full[i].cpu().numpy()
+        assert abs(got[i, 0] - metrics.psnr(ref_img, want)) <= 0.05
+        assert abs(got[i, 1] - metrics.ssim(ref_img, want)) <= 1e-3
+        assert abs(got[i, 2] - metrics.nrmse(ref_img, want)) <= 1e-3
 
 
 @pytest.mark.parametrize("variant", ["1", "2", "3"])

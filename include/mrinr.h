@@ -164,6 +164,19 @@ MRINR_API int mrinr_complex_abs(const float* d_in, int64_t n, float* d_out, void
 MRINR_API int mrinr_minmax_normalize(const float* d_in, int64_t G, int64_t n, float* d_out, float* d_scratch,
                            void* stream);
 
+/* ---- k-space front end: src/data/preprocessing.py:49-58 (apply_mask -> fastmri.ifft2c -> fastmri.complex_abs) ---- */
+/* Centred orthonormal 2-D FFT, fftshift(fft2(ifftshift(x), norm="ortho")) (inverse != 0: ifft2), of N complex images
+ * d_in [N,H,W,2] -> d_out [N,H,W,2].  Hand-written mixed-radix Stockham kernels: H, W products of 2, 3, 5, <= 1024.
+ * d_workspace: mrinr_fft2c_workspace_bytes(N,H,W) bytes.  Tolerance vs torch.fft: 2e-6 of the largest |element|. */
+MRINR_API int64_t mrinr_fft2c_workspace_bytes(int64_t N, int32_t H, int32_t W);
+MRINR_API int mrinr_fft2c(const float* d_in, int64_t N, int32_t H, int32_t W, int32_t inverse, float* d_out,
+                void* d_workspace, int64_t workspace_bytes, void* stream);
+/* load_mri_scan (preprocessing.py:33-60) after the file read: d_kspace [N,H,W,2] x column mask d_colmask [W]
+ * (nullable = fully sampled) -> ifft2c -> magnitude d_mag [N,H,W], in two HBM passes (the magnitude is fused into
+ * the column pass).  Follow with mrinr_minmax_normalize per volume (normalize_scan, preprocessing.py:127-137). */
+MRINR_API int mrinr_kspace_to_image(const float* d_kspace, const uint8_t* d_colmask, int64_t N, int32_t H, int32_t W,
+                          float* d_mag, void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- image-quality metrics of the evaluation loop: src/util/error.py:23-84 as called by metrics_error (:256-269) -- */
 /* d_original, d_predicted [N,H,W] -> d_out [N,3] (fp64): PSNR, SSIM, NRMSE per pair with the reference's data range
  * (max over both images - min over both images).  scikit-image definitions with the defaults error.py uses: SSIM

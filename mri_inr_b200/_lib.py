@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "mrinr_image_to_patches", "mrinr_classify_patches", "mrinr_patches_to_image",
     "mrinr_complex_abs", "mrinr_minmax_normalize",
     "mrinr_image_metrics_scratch_bytes", "mrinr_image_metrics",
+    "mrinr_fft2c_workspace_bytes", "mrinr_fft2c", "mrinr_kspace_to_image",
 )
 
 
@@ -94,6 +95,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrinr_image_metrics_scratch_bytes.argtypes = [c_int64]
     lib.mrinr_image_metrics.restype = c_int
     lib.mrinr_image_metrics.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.mrinr_fft2c_workspace_bytes.restype = c_int64
+    lib.mrinr_fft2c_workspace_bytes.argtypes = [c_int64, c_int32, c_int32]
+    lib.mrinr_fft2c.restype = c_int
+    lib.mrinr_fft2c.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.mrinr_kspace_to_image.restype = c_int
+    lib.mrinr_kspace_to_image.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]
     lib.mrinr_complex_abs.restype = c_int
     lib.mrinr_complex_abs.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.mrinr_minmax_normalize.restype = c_int

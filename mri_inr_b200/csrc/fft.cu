@@ -1,0 +1,287 @@
+// k-space front end: src/data/preprocessing.py:49-58 (load_mri_scan) --
+//   apply_mask (random column mask) -> fastmri.ifft2c -> fastmri.complex_abs
+// fastmri.ifft2c(x) = fftshift(ifft2(ifftshift(x), norm="ortho")) over the two image axes (fastmri/fftc.py; the
+// package is an un-vendored dependency of the reference, requirements.txt:1 -- parity against it is UNPINNED and is
+// anchored on torch.fft instead, tests/test_gpu_parity.py::test_kspace_front_end).
+//
+// Hand-written mixed-radix (2, 3, 4, 5) Stockham FFT in shared memory, two HBM passes per image:
+//   pass 1 (rows):    k-space [N,H,W] complex -> mask x ifftshift folded into the load index -> W-point transform of
+//                     8 rows per CTA -> fftshift folded into the store index -> workspace [N,H,W] complex
+//   pass 2 (columns): 8 adjacent columns per CTA (64-byte row segments), H-point transform, shift on store, and either
+//                     the complex result or its magnitude sqrt(re^2 + im^2) (one 4-byte store per pixel)
+// Algorithmic HBM bytes per pixel: 8 in + 8 out (pass 1) + 8 in + 4 out (pass 2) = 28 B (+1 B/pixel-row of mask).
+// The twiddle table exp(+-2 pi i j / n) is built per CTA with sincospif (exact argument reduction), so the
+// transform is accurate to a few fp32 ulps of the largest element.
+#include "common.cuh"
+
+namespace mrinr {
+namespace fft {
+
+constexpr int kMaxN = 1024;
+constexpr int kG = 8;              // sequences per CTA
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 12;
+
+struct Plan {
+  int n;
+  int n_stages;
+  int radix[kMaxStages];
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// R-point DFT with roots exp(sgn 2 pi i q t / R), in place
+template <int R>
+__device__ __forceinline__ void small_dft(float2 (&v)[R], float sgn) {
+  if (R == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = make_float2(a.x + b.x, a.y + b.y);
+    v[1] = make_float2(a.x - b.x, a.y - b.y);
+  } else if (R == 4) {
+    const float2 a = v[0], b = v[1], c = v[2], d = v[3];
+    const float2 s0 = make_float2(a.x + c.x, a.y + c.y), s1 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 s2 = make_float2(b.x + d.x, b.y + d.y), s3 = make_float2(b.x - d.x, b.y - d.y);
+    const float2 is3 = make_float2(-sgn * s3.y, sgn * s3.x);          // (sgn i) * (b - d)
+    v[0] = make_float2(s0.x + s2.x, s0.y + s2.y);
+    v[1] = make_float2(s1.x + is3.x, s1.y + is3.y);
+    v[2] = make_float2(s0.x - s2.x, s0.y - s2.y);
+    v[3] = make_float2(s1.x - is3.x, s1.y - is3.y);
+  } else {
+    // small prime (3, 5): u_q = sum_t v_t w^(q t), w = exp(sgn 2 pi i / R)
+    float2 w[R];
+    w[0] = make_float2(1.f, 0.f);
+    if (R == 3) {
+      w[1] = make_float2(-0.5f, sgn * 0.86602540378443865f);
+      w[2] = make_float2(-0.5f, -sgn * 0.86602540378443865f);
+    } else {
+      w[1] = make_float2(0.30901699437494742f, sgn * 0.95105651629515357f);
+      w[2] = make_float2(-0.80901699437494742f, sgn * 0.58778525229247313f);
+      w[R - 2] = make_float2(-0.80901699437494742f, -sgn * 0.58778525229247313f);
+      w[R - 1] = make_float2(0.30901699437494742f, -sgn * 0.95105651629515357f);
+    }
+    float2 u[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      float2 acc = v[0];
+#pragma unroll
+      for (int t = 1; t < R; ++t) {
+        const float2 p = cmul(v[t], w[(q * t) % R]);
+        acc.x += p.x;
+        acc.y += p.y;
+      }
+      u[q] = acc;
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = u[q];
+  }
+}
+
+// One Stockham pass of radix R over kG sequences of length n held in shared memory.
+// Element i of sequence g lives at x[g * ss + i * es]; COLS selects which index runs fastest across threads.
+template <int R, bool COLS>
+__device__ __forceinline__ void stage(const float2* __restrict__ x, float2* __restrict__ y, int n, int Ns, int ss, int es,
+                                      const float2* __restrict__ tw, float sgn) {
+  const int nb = n / R;
+  const int tstep = n / (Ns * R);
+  for (int w = threadIdx.x; w < nb * kG; w += kThreads) {
+    int g, j;
+    if (COLS) { g = w % kG; j = w / kG; } else { g = w / nb; j = w - g * nb; }
+    const int k = j % Ns;
+    float2 v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+      v[t] = x[g * ss + (j + t * nb) * es];
+      if (t > 0) v[t] = cmul(v[t], tw[t * k * tstep]);
+    }
+    small_dft<R>(v, sgn);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int q = 0; q < R; ++q) y[g * ss + (j0 + q * Ns) * es] = v[q];
+  }
+}
+
+template <bool COLS>
+__device__ __forceinline__ const float2* run_stages(float2* a, float2* b, const Plan& plan, int ss, int es, const float2* tw,
+                                                    float sgn) {
+  int Ns = 1;
+  float2* x = a;
+  float2* y = b;
+  for (int s = 0; s < plan.n_stages; ++s) {
+    const int r = plan.radix[s];
+    if (r == 4) stage<4, COLS>(x, y, plan.n, Ns, ss, es, tw, sgn);
+    else if (r == 2) stage<2, COLS>(x, y, plan.n, Ns, ss, es, tw, sgn);
+    else if (r == 3) stage<3, COLS>(x, y, plan.n, Ns, ss, es, tw, sgn);
+    else stage<5, COLS>(x, y, plan.n, Ns, ss, es, tw, sgn);
+    Ns *= r;
+    __syncthreads();
+    float2* t = x; x = y; y = t;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void build_twiddles(float2* tw, int n, float sgn) {
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    float s, c;
+    sincospif(2.0f * (float)i / (float)n, &s, &c);
+    tw[i] = make_float2(c, sgn * s);
+  }
+}
+
+// rows: in [n_rows, n] complex -> out [n_rows, n] complex; centred (shift by n/2 on both sides), orthonormal
+__global__ void __launch_bounds__(kThreads)
+rows_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmask, float2* __restrict__ out, long long n_rows,
+            Plan plan, float sgn, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int n = plan.n;
+  const int ss = n + 1;
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* a = tw + n;
+  float2* b = a + kG * ss;
+  build_twiddles(tw, n, sgn);
+  const long long row0 = (long long)blockIdx.x * kG;
+  const int half = n / 2;
+  for (int w = threadIdx.x; w < kG * n; w += kThreads) {
+    const int g = w / n, i = w - g * n;            // i = index in the source row (coalesced)
+    float2 v = make_float2(0.f, 0.f);
+    if (row0 + g < n_rows) {
+      v = __ldg(in + (row0 + g) * n + i);
+      if (colmask && !colmask[i]) v = make_float2(0.f, 0.f);
+    }
+    // ifftshift: a[m] = src[(m + n/2) % n]  <=>  source index i goes to m = (i - n/2) mod n
+    int m = i - half;
+    if (m < 0) m += n;
+    a[g * ss + m] = v;
+  }
+  __syncthreads();
+  const float2* r = run_stages<false>(a, b, plan, ss, 1, tw, sgn);
+  for (int w = threadIdx.x; w < kG * n; w += kThreads) {
+    const int g = w / n, o = w - g * n;            // o = index in the destination row (coalesced)
+    if (row0 + g >= n_rows) continue;
+    // fftshift: out[o] = r[(o - n/2) mod n]
+    int m = o - half;
+    if (m < 0) m += n;
+    const float2 v = r[g * ss + m];
+    out[(row0 + g) * n + o] = make_float2(v.x * scale, v.y * scale);
+  }
+}
+
+// columns: in [N, H, W] complex, transform along H for kG adjacent columns; complex or magnitude output
+template <bool ABS>
+__global__ void __launch_bounds__(kThreads)
+cols_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __restrict__ out_abs, int H, int W, Plan plan,
+            float sgn, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int n = plan.n;                           // == H
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* a = tw + n;
+  float2* b = a + kG * n;
+  build_twiddles(tw, n, sgn);
+  const long long img = blockIdx.y;
+  const int x0 = blockIdx.x * kG;
+  const float2* src = in + img * (long long)H * W;
+  const int half = n / 2;
+  for (int w = threadIdx.x; w < kG * n; w += kThreads) {
+    const int g = w % kG, i = w / kG;              // g fastest: 64-byte row segments
+    float2 v = make_float2(0.f, 0.f);
+    if (x0 + g < W) v = __ldg(src + (long long)i * W + x0 + g);
+    int m = i - half;
+    if (m < 0) m += n;
+    a[m * kG + g] = v;
+  }
+  __syncthreads();
+  const float2* r = run_stages<true>(a, b, plan, 1, kG, tw, sgn);
+  for (int w = threadIdx.x; w < kG * n; w += kThreads) {
+    const int g = w % kG, o = w / kG;
+    if (x0 + g >= W) continue;
+    int m = o - half;
+    if (m < 0) m += n;
+    float2 v = r[m * kG + g];
+    v.x *= scale;
+    v.y *= scale;
+    const long long dst = img * (long long)H * W + (long long)o * W + x0 + g;
+    if (ABS) out_abs[dst] = sqrtf(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));   // fastmri.complex_abs
+    else out_c[dst] = v;
+  }
+}
+
+static bool make_plan(int n, Plan* p) {
+  if (n < 2 || n > kMaxN) return false;
+  p->n = n;
+  p->n_stages = 0;
+  int m = n;
+  const int radices[4] = {4, 2, 3, 5};
+  for (int ri = 0; ri < 4; ++ri) {
+    const int r = radices[ri];
+    while (m % r == 0) {
+      if (p->n_stages == kMaxStages) return false;
+      p->radix[p->n_stages++] = r;
+      m /= r;
+    }
+  }
+  return m == 1;
+}
+
+static int run(const float* d_in, const uint8_t* d_colmask, long long N, int H, int W, int inverse, float* d_out_c,
+               float* d_out_abs, void* d_ws, cudaStream_t st) {
+  Plan pw, ph;
+  MRINR_REQUIRE(make_plan(W, &pw) && make_plan(H, &ph), MRINR_E_UNSUPPORTED,
+                "fft2c: sizes must be products of 2, 3 and 5 in [2, %d] (got %d x %d)", kMaxN, H, W);
+  const float sgn = inverse ? 1.f : -1.f;
+  const size_t smem_r = (size_t)(W + 2 * kG * (W + 1)) * sizeof(float2);
+  const size_t smem_c = (size_t)(H + 2 * kG * H) * sizeof(float2);
+  MRINR_CUDA(cudaFuncSetAttribute(rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+  MRINR_CUDA(cudaFuncSetAttribute(cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  MRINR_CUDA(cudaFuncSetAttribute(cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  const long long n_rows = N * H;
+  float2* tmp = static_cast<float2*>(d_ws);
+  rows_kernel<<<(unsigned)((n_rows + kG - 1) / kG), kThreads, smem_r, st>>>(reinterpret_cast<const float2*>(d_in), d_colmask, tmp,
+                                                                         n_rows, pw, sgn, 1.0f / sqrtf((float)W));
+  dim3 grid((W + kG - 1) / kG, (unsigned)N);
+  if (d_out_abs)
+    cols_kernel<true><<<grid, kThreads, smem_c, st>>>(tmp, nullptr, d_out_abs, H, W, ph, sgn, 1.0f / sqrtf((float)H));
+  else
+    cols_kernel<false><<<grid, kThreads, smem_c, st>>>(tmp, reinterpret_cast<float2*>(d_out_c), nullptr, H, W, ph, sgn,
+                                                     1.0f / sqrtf((float)H));
+  count_launch(2);
+  return check_launch("fft2c");
+}
+
+}  // namespace fft
+}  // namespace mrinr
+
+using namespace mrinr;
+
+extern "C" int64_t mrinr_fft2c_workspace_bytes(int64_t N, int32_t H, int32_t W) {
+  if (N < 0 || H < 0 || W < 0) return 0;
+  return (int64_t)((size_t)N * H * W * sizeof(float2));
+}
+
+static int check_fft_args(const char* who, const void* in, const void* out, const void* ws, int64_t N, int32_t H, int32_t W,
+                          int64_t ws_bytes) {
+  MRINR_REQUIRE(in && out && ws, MRINR_E_ARG, "%s: null pointer", who);
+  MRINR_REQUIRE(N > 0 && N <= 65535, MRINR_E_ARG, "%s: between 1 and 65535 images per call (got %lld)", who, (long long)N);
+  MRINR_REQUIRE(ws_bytes >= mrinr_fft2c_workspace_bytes(N, H, W), MRINR_E_ARG,
+                "%s: workspace must hold mrinr_fft2c_workspace_bytes(N,H,W) bytes", who);
+  MRINR_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(ws) & 7u) == 0,
+                MRINR_E_ALIGN, "%s: buffers must be 8-byte aligned", who);
+  return 0;
+}
+
+extern "C" int mrinr_fft2c(const float* d_in, int64_t N, int32_t H, int32_t W, int32_t inverse, float* d_out,
+                           void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (N == 0) return 0;
+  const int rc = check_fft_args("mrinr_fft2c", d_in, d_out, d_workspace, N, H, W, workspace_bytes);
+  if (rc != 0) return rc;
+  return fft::run(d_in, nullptr, N, H, W, inverse, d_out, nullptr, d_workspace, (cudaStream_t)stream);
+}
+
+extern "C" int mrinr_kspace_to_image(const float* d_kspace, const uint8_t* d_colmask, int64_t N, int32_t H, int32_t W,
+                                     float* d_mag, void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (N == 0) return 0;
+  const int rc = check_fft_args("mrinr_kspace_to_image", d_kspace, d_mag, d_workspace, N, H, W, workspace_bytes);
+  if (rc != 0) return rc;
+  return fft::run(d_kspace, d_colmask, N, H, W, /*inverse*/ 1, nullptr, d_mag, d_workspace, (cudaStream_t)stream);
+}

@@ -327,3 +327,49 @@ def image_metrics(original: torch.Tensor, predicted: torch.Tensor) -> torch.Tens
                                            scratch.data_ptr(), scratch.numel() * 8, _lib.stream_ptr(original.device)),
                    "image_metrics")
     return out
+
+
+def _fft_args(x: torch.Tensor, name: str):
+    _lib.require_cuda(x, name, torch.float32)
+    if x.dim() == 3:
+        x = x[None]
+    if x.dim() != 4 or x.shape[-1] != 2:
+        raise RuntimeError(f"{name} must be [N,H,W,2] or [H,W,2] (real, imag), got {tuple(x.shape)}")
+    return x.contiguous()
+
+
+def fft2c(x: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """Centred orthonormal 2-D FFT of ``[N,H,W,2]`` (``fastmri.fft2c`` / ``ifft2c``): ``fftshift(fft2(ifftshift(x),
+    norm="ortho"))`` over H and W, on the hand-written Stockham kernels (sizes: products of 2, 3, 5 up to 1024)."""
+    lib = _lib.load()
+    squeeze = x.dim() == 3
+    x = _fft_args(x, "x")
+    N, H, W, _ = x.shape
+    out = torch.empty_like(x)
+    ws = torch.empty(max(1, int(lib.mrinr_fft2c_workspace_bytes(N, H, W)) // 4), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mrinr_fft2c(x.data_ptr(), N, H, W, 1 if inverse else 0, out.data_ptr(), ws.data_ptr(),
+                                   ws.numel() * 4, _lib.stream_ptr(x.device)), "fft2c")
+    return out[0] if squeeze else out
+
+
+def kspace_to_image(kspace: torch.Tensor, column_mask: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``load_mri_scan`` after the file read (src/data/preprocessing.py:49-58): k-space ``[N,H,W,2]`` x column mask
+    ``[W]`` (bool / uint8, None = fully sampled) -> ``fastmri.ifft2c`` -> ``fastmri.complex_abs`` -> ``[N,H,W]``."""
+    lib = _lib.load()
+    squeeze = kspace.dim() == 3
+    k = _fft_args(kspace, "kspace")
+    N, H, W, _ = k.shape
+    mask = None
+    if column_mask is not None:
+        mask = _lib.require_cuda(column_mask, "column_mask").to(torch.uint8).contiguous()
+        if mask.numel() != W:
+            raise RuntimeError(f"column_mask must have {W} entries, got {mask.numel()}")
+    if out is None:
+        out = torch.empty(N, H, W, dtype=torch.float32, device=k.device)
+    ws = torch.empty(max(1, int(lib.mrinr_fft2c_workspace_bytes(N, H, W)) // 4), dtype=torch.float32, device=k.device)
+    with torch.cuda.device(k.device):
+        _lib.check(lib.mrinr_kspace_to_image(k.data_ptr(), _ptr(mask), N, H, W, out.data_ptr(), ws.data_ptr(),
+                                             ws.numel() * 4, _lib.stream_ptr(k.device)), "kspace_to_image")
+    return out[0] if squeeze else out

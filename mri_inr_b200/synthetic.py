@@ -2,8 +2,8 @@
 
 Follows the reference's preprocessing chain (src/data/preprocessing.py:33-60,127-137): k-space -> random column
 mask (acceleration / center fraction) -> centred orthonormal inverse FFT -> magnitude -> per-volume min-max
-normalisation.  The FFT is ``torch.fft`` (cuFFT; set-up only, never inside a timed region); magnitude and
-normalisation run on this package's kernels.
+normalisation.  The k-space front end -- mask, centred inverse FFT, magnitude (``ops.kspace_to_image``) and the
+normalisation -- runs on this package's kernels; ``torch.fft`` (cuFFT) is only used to *make* the phantom's k-space.
 """
 from __future__ import annotations
 
@@ -57,11 +57,9 @@ def synthetic_slices(n_slices: int, height: int = 320, width: int = 320, *, devi
         ay = 0.65 + 0.3 * torch.rand(n, 1, 1, device=device, generator=gen)
         support = ((xx / ax) ** 2 + (yy / ay) ** 2 <= 1.0).to(torch.float32)
         phantom = (field - field.amin(dim=(1, 2), keepdim=True)) * support
-        k = _fft2c(phantom.to(torch.complex64))
-        if undersampled:
-            k = k * mask
-        img = torch.view_as_real(_ifft2c(k)).contiguous()
-        mag = ops.complex_abs(img)
+        k = torch.view_as_real(_fft2c(phantom.to(torch.complex64))).contiguous()
+        # load_mri_scan (preprocessing.py:49-58): apply_mask -> ifft2c -> complex_abs
+        mag = ops.kspace_to_image(k, mask if undersampled else None)
         # per-volume normalisation (preprocessing.py:127-137); a trailing partial volume is its own group
         full = (n // slices_per_volume) * slices_per_volume
         if full:

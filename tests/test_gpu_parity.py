@@ -385,6 +385,53 @@ def test_image_metrics_match_oracle(hw):
     assert abs(metrics.calculate_data_range(a, b) - ometrics.data_range(full[1], pred[1])) < 1e-6
 
 
+@pytest.mark.parametrize("hw", [(320, 320), (64, 80), (30, 50), (96, 75), (1024, 8), (2, 2)])
+def test_fft2c_matches_torch_fft(hw):
+    """mrinr_fft2c (hand-written Stockham kernels) against torch.fft with fastmri's centring convention
+    fftshift(fft2(ifftshift(x), norm="ortho")); even, odd and mixed-radix (2, 3, 5) sizes; 2e-6 of the largest element."""
+    from mri_inr_b200 import ops
+
+    h, w = hw
+    rs = np.random.RandomState(h * 7 + w)
+    x = torch.from_numpy(rs.normal(size=(3, h, w, 2)).astype(np.float32)).to(DEV)
+    xc = torch.view_as_complex(x)
+    for inverse in (False, True):
+        f = torch.fft.ifft2 if inverse else torch.fft.fft2
+        want = torch.fft.fftshift(f(torch.fft.ifftshift(xc, dim=(-2, -1)), norm="ortho"), dim=(-2, -1))
+        got = torch.view_as_complex(ops.fft2c(x, inverse=inverse))
+        err = float((got - want).abs().max() / want.abs().max())
+        print(f"{hw} inverse={inverse}: rel err {err:.2e}")
+        assert err <= 2e-6
+    # round trip and Parseval (size-independent properties)
+    back = ops.fft2c(ops.fft2c(x), inverse=True)
+    assert float((back - x).abs().max()) <= 5e-6 * float(x.abs().max())
+    assert abs(float((ops.fft2c(x) ** 2).sum() / (x ** 2).sum()) - 1.0) <= 1e-5
+
+
+def test_kspace_front_end():
+    """load_mri_scan after the file read (preprocessing.py:49-58): mask -> ifft2c -> complex_abs, then normalize_scan
+    per volume (:127-137), against the same chain in torch.fft / numpy."""
+    from mri_inr_b200 import ops
+    from mri_inr_b200.synthetic import column_mask
+
+    rs = np.random.RandomState(9)
+    k = torch.from_numpy(rs.normal(size=(22, 320, 320, 2)).astype(np.float32)).to(DEV)
+    mask = torch.from_numpy(column_mask(320, 6, 0.05, 1234)).to(DEV)
+    got = ops.kspace_to_image(k, mask)
+    kc = torch.view_as_complex(k) * mask
+    want = torch.fft.fftshift(torch.fft.ifft2(torch.fft.ifftshift(kc, dim=(-2, -1)), norm="ortho"), dim=(-2, -1)).abs()
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.max())
+    full = ops.kspace_to_image(k, None)
+    want_full = torch.fft.fftshift(torch.fft.ifft2(torch.fft.ifftshift(torch.view_as_complex(k), dim=(-2, -1)),
+                                                   norm="ortho"), dim=(-2, -1)).abs()
+    assert float((full - want_full).abs().max()) <= 2e-6 * float(want_full.max())
+    # per-volume normalisation of the kernel's own magnitudes is bit-exact against normalize_scan
+    norm = ops.minmax_normalize(got, groups=2).cpu().numpy()
+    g = got.cpu().numpy()
+    for v in range(2):
+        assert np.array_equal(norm[v * 11:(v + 1) * 11], otiling.normalize_scan(g[v * 11:(v + 1) * 11]))
+
+
 def test_cpu_tensors_and_grad_are_refused():
     name, sd_kw, act, model_kw = MODEL_CASES[0]
     m, sd = _model(sd_kw, act, model_kw, "fp16")

@@ -144,6 +144,50 @@ patches_to_image_kernel(const float* __restrict__ tiles, const float* __restrict
   out[gid] = __fdiv_rn(acc, norm);
 }
 
+// Same gather, four adjacent output pixels per thread (one 16-byte store, 16-byte tile and weight loads).
+// Valid when I, K and padq = (K-I)/2 are multiples of 4: the set of patches covering a pixel only changes at
+// x + padq = 0 or K - I (mod I), both multiples of 4, so an aligned group of four pixels shares its patch set and
+// its tile-row offsets are 16-byte aligned.  Per pixel the additions happen in the scalar kernel's order, so the
+// result is bit-identical.
+__global__ void __launch_bounds__(256)
+patches_to_image_vec4_kernel(const float* __restrict__ tiles, const float* __restrict__ weights,
+                             const uint8_t* __restrict__ black, long long n_quads, int nV, int nH, int K, int I,
+                             float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_quads) return;
+  const int OH = nV * I, OW4 = (nH * I) >> 2;
+  const int per_img = OH * OW4;
+  const long long n = gid / per_img;
+  const int rem = (int)(gid - n * per_img);
+  const int y = rem / OW4, x = (rem - y * OW4) << 2;
+  const int padq = (K - I) / 2;
+  const int yp = y + padq, xp = x + padq;
+  const int py_hi = min(yp / I, nV - 1);
+  const int py_lo = (yp - K + 1 <= 0) ? 0 : (yp - K + I) / I;
+  const int px_hi = min(xp / I, nH - 1);
+  const int px_lo = (xp + 3 - K + 1 <= 0) ? 0 : (xp + 3 - K + I) / I;     // same for all four pixels of the group
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), norm = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long pbase = n * (long long)nV * nH;
+  const int KK = K * K;
+  for (int py = py_hi; py >= py_lo; --py) {
+    const int ky = yp - I * py;
+    for (int px = px_hi; px >= px_lo; --px) {
+      const int kx = xp - I * px;
+      const long long p = pbase + py * nH + px;
+      float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (weights) w = __ldg(reinterpret_cast<const float4*>(weights + ky * K + kx));
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (black == nullptr || black[p] == 0) t = __ldg(reinterpret_cast<const float4*>(tiles + p * KK + ky * K + kx));
+      acc.x = __fadd_rn(acc.x, __fmul_rn(t.x, w.x)); norm.x = __fadd_rn(norm.x, w.x);
+      acc.y = __fadd_rn(acc.y, __fmul_rn(t.y, w.y)); norm.y = __fadd_rn(norm.y, w.y);
+      acc.z = __fadd_rn(acc.z, __fmul_rn(t.z, w.z)); norm.z = __fadd_rn(norm.z, w.z);
+      acc.w = __fadd_rn(acc.w, __fmul_rn(t.w, w.w)); norm.w = __fadd_rn(norm.w, w.w);
+    }
+  }
+  reinterpret_cast<float4*>(out)[gid] = make_float4(__fdiv_rn(acc.x, norm.x), __fdiv_rn(acc.y, norm.y),
+                                                    __fdiv_rn(acc.z, norm.z), __fdiv_rn(acc.w, norm.w));
+}
+
 // ------------------------------------------------------------------------------------------------
 // complex magnitude (fastmri.complex_abs at preprocessing.py:58): sqrt(re^2 + im^2), with the two
 // squares rounded separately as torch's (data**2).sum(-1).sqrt() does.
@@ -390,6 +434,14 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
                 "mrinr_patches_to_image: bad sizes (K=%d I=%d)", K, I);
   if (N == 0) return 0;
   const long long n_pix = (long long)N * nV * I * nH * I;
+  if (I % 4 == 0 && K % 4 == 0 && ((K - I) / 2) % 4 == 0 && aligned16(d_tiles) && aligned16(d_img) &&
+      (d_weights == nullptr || aligned16(d_weights))) {
+    const long long n_quads = n_pix / 4;
+    patches_to_image_vec4_kernel<<<(unsigned)((n_quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_tiles, d_weights, d_black, n_quads, nV, nH, K, I, d_img);
+    count_launch();
+    return check_launch("patches_to_image_vec4");
+  }
   patches_to_image_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       d_tiles, d_weights, d_black, n_pix, nV, nH, K, I, d_img);
   count_launch();

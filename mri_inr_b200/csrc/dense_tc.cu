@@ -13,27 +13,40 @@
 // accumulated in fp32 in TMEM: ~1e-6 relative, i.e. the noise level of an fp32 FFMA loop with a different summation
 // order.  tests/test_gpu_parity.py holds the result to 1e-5 against the reference.
 //
-// Per CTA: one 128-row tile, all N columns (N = 64, 128 or 256), K in slabs of 64 through a 2-stage ring.
+// Per CTA: one 128-row tile, all N columns (N = 64, 128 or 256), K in slabs of 32 through a 2-stage ring (96 KB for
+// N = 256), so that TWO CTAs are resident per SM: one CTA's prologue / epilogue (all latency) hides behind the
+// other's MMAs.  (With one 192 KB CTA per SM the tensor pipe was 18 % active, profiles/r01_ncu_dense_split.txt.)
 //   warps 0-3  A producers: thread = row; load 64 fp32 (one slab ahead, in registers), split, write both halves in
 //              the UMMA K-major core-matrix layout; afterwards the epilogue (tcgen05.ld, bias, activation, store)
 //   warp 4     MMA issuer (converged warp + elect.sync); owns the TMEM allocation
 //   warp 5     weight producer: one cp.async.bulk per slab (hi and lo halves are contiguous in the packed array)
+// Clusters of kCluster CTAs share the weights: every CTA fetches 1/kCluster of a slab and MULTICASTS it into the same
+// shared-memory offset of all CTAs of the cluster (cp.async.bulk ... .multicast::cluster), so the L2 -> SM weight
+// traffic per row tile drops by kCluster (the kernel is bound by L2 delivery: 64 KB of weights per 32 KB of operand
+// rows without it).  A stage may only be refilled when the MMAs of ALL CTAs have consumed it, so the tensor core's
+// completion (tcgen05.commit) is multicast too: the `empty` barrier of every CTA counts kCluster arrivals.
 #include "tc_ptx.cuh"
 
 namespace mrinr {
 namespace dense {
 
 constexpr int kBM = 128;
-constexpr int kSlabK = 64;
+constexpr int kSlabK = 32;
+constexpr int kKc = kSlabK / 8;    // 16-byte K chunks per slab
 constexpr int kStages = 2;
 constexpr int kThreads = 192;
-constexpr int kAHalfBytes = kBM * kSlabK * 2;          // 16 KB: [8 kc][128 rows][8] fp16
+#ifndef MRINR_DENSE_CLUSTER
+#define MRINR_DENSE_CLUSTER 2
+#endif
+constexpr int kCluster = MRINR_DENSE_CLUSTER;
+constexpr int kAHalfBytes = kBM * kSlabK * 2;          // 8 KB: [4 kc][128 rows][8] fp16
 
 template <int N>
 struct Cfg {
-  static constexpr int kWHalfBytes = N * kSlabK * 2;   // [8 kc][N][8] fp16
+  static constexpr int kWHalfBytes = N * kSlabK * 2;   // [4 kc][N][8] fp16
   static constexpr int kStageBytes = 2 * kAHalfBytes + 2 * kWHalfBytes;
-  static constexpr int kOffBar = kStages * kStageBytes;
+  static constexpr int kOffBias = kStages * kStageBytes;          // [N] f32
+  static constexpr int kOffBar = kOffBias + N * 4;
   static constexpr int kSmemBytes = kOffBar + 64 + 16;
   static constexpr int kTmemCols = N < 32 ? 32 : N;
 };
@@ -50,20 +63,20 @@ struct DenseParams {
   int32_t* errflag;
 };
 
-// W [N, K] fp32 row-major (nn.Linear / flattened Conv2d weight) -> [K/64 slabs][hi, lo][8 kc][N][8] fp16
+// W [N, K] fp32 row-major (nn.Linear / flattened Conv2d weight) -> [K/32 slabs][hi, lo][4 kc][N][8] fp16
 __global__ void pack_split_kernel(const float* __restrict__ w, int N, int K, uint16_t* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * K) return;
   const int e = (int)(i & 7);
   const int n = (int)((i >> 3) % N);
-  const int kc = (int)(((i >> 3) / N) & 7);
-  const int slab = (int)((i >> 3) / N) >> 3;
+  const int kc = (int)(((i >> 3) / N) % kKc);
+  const int slab = (int)(((i >> 3) / N) / kKc);
   const float x = w[(long long)n * K + slab * kSlabK + kc * 8 + e];
   const __half hi = __float2half_rn(x);
   const __half lo = __float2half_rn(x - __half2float(hi));
-  const long long base = (long long)slab * 2 * 8 * N * 8 + ((long long)kc * N + n) * 8 + e;
+  const long long base = (long long)slab * 2 * kKc * N * 8 + ((long long)kc * N + n) * 8 + e;
   out[base] = *reinterpret_cast<const uint16_t*>(&hi);
-  out[base + (long long)8 * N * 8] = *reinterpret_cast<const uint16_t*>(&lo);
+  out[base + (long long)kKc * N * 8] = *reinterpret_cast<const uint16_t*>(&lo);
 }
 
 __device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& hi, uint4& lo) {
@@ -82,7 +95,7 @@ __device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& 
 }
 
 template <int N>
-__global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DenseParams P) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) dense_split_kernel(const DenseParams P) {
   using C = Cfg<N>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -97,12 +110,14 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
   auto bar_empty = [&](int s) { return bar0 + 8u * (uint32_t)(4 + s); };
   const uint32_t bar_acc = bar0 + 8u * 6u;
   const int n_slabs = (P.K1 + P.K2) / kSlabK;
+  float* s_bias = reinterpret_cast<float*>(smem + C::kOffBias);
+  for (int i = tid; i < N; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_afull(s), 4);
       mbar_init(bar_wfull(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), kCluster);
     }
     mbar_init(bar_acc, 1);
     fence_barrier_init();
@@ -110,20 +125,22 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
   if (warp == 4) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // every CTA's barriers exist before a peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const uint32_t crank = cluster_ctarank();
 
   if (warp < 4) {
     // =========================== A producers, then epilogue ===========================
     const long long row = (long long)blockIdx.x * kBM + tid;
     const bool live = row < P.M;
-    auto load_slab = [&](int slab, float4 (&r)[16]) {
+    auto load_slab = [&](int slab, float4 (&r)[2 * kKc]) {
       const int k = slab * kSlabK;
       const float* src = (k < P.K1) ? P.a1 + row * P.lda1 + k : P.a2 + row * P.lda2 + (k - P.K1);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = live ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 2 * kKc; ++i) r[i] = live ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    float4 r[16];
+    float4 r[2 * kKc];
     if (n_slabs > 0) load_slab(0, r);
     for (int slab = 0; slab < n_slabs; ++slab) {
       const int st = slab % kStages;
@@ -131,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
       uint8_t* a_hi = smem + st * C::kStageBytes;
       uint8_t* a_lo = a_hi + kAHalfBytes;
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int kc = 0; kc < kKc; ++kc) {
         uint4 hi, lo;
         split8(r[2 * kc], r[2 * kc + 1], hi, lo);
         *reinterpret_cast<uint4*>(a_hi + kc * (kBM * 16) + tid * 16) = hi;
@@ -156,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float x = __uint_as_float(v[i]);
-        if (P.bias) x += __ldg(P.bias + c0 + i);
+        x += s_bias[c0 + i];
         if (P.act == 1) x = fmaxf(x, 0.f);
         else if (P.act == 2) x = x > 0.f ? x : x * P.slope;
         y[i] = x;
@@ -184,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
         const uint64_t b_hi = make_smem_desc(sa + 2 * kAHalfBytes, N * 16, 128);
         const uint64_t b_lo = make_smem_desc(sa + 2 * kAHalfBytes + C::kWHalfBytes, N * 16, 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kSlabK / 16; ++k) {
           const uint64_t da = (uint64_t)((k * 2 * kBM * 16) >> 4);
           const uint64_t db = (uint64_t)((k * 2 * N * 16) >> 4);
           // small terms first
@@ -192,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
           umma_f16(tmem_base, a_hi + da, b_lo + db, idesc, 1u);
           umma_f16(tmem_base, a_hi + da, b_hi + db, idesc, 1u);
         }
-        umma_commit(bar_empty(st));
+        umma_commit_mc(bar_empty(st), (uint16_t)((1u << kCluster) - 1u));   // frees the stage in every CTA
         if (slab == n_slabs - 1) umma_commit(bar_acc);
       }
       __syncwarp();
@@ -203,10 +220,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
       for (int slab = 0; slab < n_slabs; ++slab) {
         const int st = slab % kStages;
         mbar_wait_backoff(bar_empty(st), ((slab / kStages) & 1u) ^ 1u, P.errflag, 25);
-        mbar_expect_tx(bar_wfull(st), 2u * C::kWHalfBytes);
-        bulk_g2s(smem_u32(smem + st * C::kStageBytes + 2 * kAHalfBytes),
-                 reinterpret_cast<const uint8_t*>(P.w) + (size_t)slab * 2 * C::kWHalfBytes, 2u * C::kWHalfBytes,
-                 bar_wfull(st));
+        mbar_expect_tx(bar_wfull(st), 2u * C::kWHalfBytes);                       // the whole slab lands here ...
+        constexpr uint32_t part = 2u * C::kWHalfBytes / kCluster;                  // ... in kCluster multicast pieces
+        bulk_g2s_mc(smem_u32(smem + st * C::kStageBytes + 2 * kAHalfBytes) + crank * part,
+                    reinterpret_cast<const uint8_t*>(P.w) + (size_t)slab * 2 * C::kWHalfBytes + (size_t)crank * part, part,
+                    bar_wfull(st), (uint16_t)((1u << kCluster) - 1u));
       }
     }
     __syncwarp();
@@ -214,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_split_kernel(const DensePar
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // no CTA may exit while a peer can still multicast into its shared memory
   tc_fence_after();
   if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
 }
@@ -225,7 +244,8 @@ static int launch_n(const DenseParams& P, cudaStream_t st) {
     MRINR_CUDA(cudaFuncSetAttribute(dense_split_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<N>::kSmemBytes));
     configured = true;
   }
-  const long long grid = (P.M + kBM - 1) / kBM;
+  long long grid = (P.M + kBM - 1) / kBM;
+  grid = (grid + kCluster - 1) / kCluster * kCluster;      // whole clusters; the extra CTAs only help with the weights
   dense_split_kernel<N><<<(unsigned)grid, kThreads, Cfg<N>::kSmemBytes, st>>>(P);
   count_launch();
   return check_launch("dense_split");

@@ -432,6 +432,56 @@ def test_kspace_front_end():
         assert np.array_equal(norm[v * 11:(v + 1) * 11], otiling.normalize_scan(g[v * 11:(v + 1) * 11]))
 
 
+def test_kernels_stay_inside_their_output_buffers():
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are checked with guard bands: every output
+    buffer is a window of a larger allocation pre-filled with a sentinel; after the call the margins must be
+    untouched.  Batch sizes are chosen ragged with respect to every tile size (4-patch conv pass, 128-row product
+    tile, 2-CTA clusters, 4-tile synthesis iterations, 32x32 SSIM tiles, 8-row FFT groups)."""
+    from mri_inr_b200 import ops
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    packed = m._packed()
+    G = 4096                                           # guard elements on each side
+    SENT = 1234.5
+
+    def guarded(*shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        big = torch.full((n + 2 * G,), SENT, dtype=dtype, device=DEV)
+        return big, big[G:G + n].view(*shape)
+
+    def check(big, what):
+        assert bool((big[:G] == SENT).all()) and bool((big[-G:] == SENT).all()), f"{what}: wrote outside its buffer"
+
+    for B in (1, 5, 131, 259):
+        tiles = torch.from_numpy(synth_tiles(300 + B, B)).to(DEV)
+        zb, z = guarded(B, 256)
+        ops.encoder_forward(packed, tiles, out=z)
+        check(zb, f"encoder_forward B={B}")
+        mb, mods = guarded(5, B, 256)
+        ops.modulator_forward(packed, z, out=mods)
+        check(mb, f"modulator_forward B={B}")
+        ob, out = guarded(B, 576)
+        black = torch.zeros(B, dtype=torch.uint8, device=DEV)
+        black[::3] = 1
+        ops.siren_forward(packed, mods, out=out)
+        check(ob, f"siren_forward B={B}")
+        ops.siren_forward(packed, mods, black=black, out=out)
+        check(ob, f"siren_forward (black mask) B={B}")
+        assert bool(torch.isfinite(out).all()) and bool((out[::3] == 0).all())
+    img = torch.from_numpy(np.stack([synth_image(60 + i, 80, 112) for i in range(3)])).to(DEV)
+    pb, patches = guarded(3 * 5 * 7, 32, 32)
+    ops.image_to_patches(img, 32, 16, out=patches)
+    check(pb, "image_to_patches")
+    rb, rec = guarded(3, 80, 112)
+    ops.patches_to_image(torch.rand(3 * 35, 24, 24, device=DEV), 3, (5, 7), 16, out=rec)
+    check(rb, "patches_to_image")
+    kb, mag = guarded(3, 30, 50)
+    ops.kspace_to_image(torch.randn(3, 30, 50, 2, device=DEV), None, out=mag)
+    check(kb, "kspace_to_image")
+    torch.cuda.synchronize()
+
+
 def test_cpu_tensors_and_grad_are_refused():
     name, sd_kw, act, model_kw = MODEL_CASES[0]
     m, sd = _model(sd_kw, act, model_kw, "fp16")

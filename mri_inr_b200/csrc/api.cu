@@ -43,6 +43,7 @@ extern "C" int64_t mrinr_launch_count(void) { return (int64_t)g_launches.load();
 extern "C" void mrinr_free_packed(MrinrPacked* p) {
   if (!p) return;
   cudaFree(p->d_table0);
+  cudaFree(p->d_table16);
   cudaFree(p->d_net_wT);
   cudaFree(p->d_net_w16);
   cudaFree(p->d_net_w16p);
@@ -136,6 +137,7 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
   {
     const size_t mod_w_elems = (size_t)Z * H + (size_t)(L - 1) * (H + Z) * H;
     PK_CUDA(cudaMalloc(&p->d_table0, (size_t)C * H * sizeof(float)));
+    PK_CUDA(cudaMalloc(&p->d_table16, (size_t)C * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_wT, (size_t)(L - 1) * H * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_w16, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_w16p, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
@@ -162,6 +164,7 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     if (b0) PK_CUDA(cudaMemcpyAsync(p->d_layer0 + 2 * H, b0, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PK_CUDA(cudaMemcpyAsync(p->d_grid, v->d_grid, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PK_RC(run_layer0_table(v->d_grid, v->d_net_weight[0], b0, C, H, p->w0_initial, p->activation, p->d_table0, st));
+    PK_RC(run_table16(p->d_table0, (long long)C * H, precision == MRINR_PREC_BF16, p->d_table16, st));
     for (int l = 0; l < L; ++l) {
       if (v->d_net_bias && v->d_net_bias[l])
         PK_CUDA(cudaMemcpyAsync(p->d_net_bias + (size_t)l * H, v->d_net_bias[l], H * sizeof(float),

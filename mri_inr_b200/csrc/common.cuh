@@ -45,6 +45,7 @@ struct MrinrPacked {
   int32_t device;
   int32_t num_sms;
   float*    d_table0;    // [C,H]  act_0(W_0 g_c + b_0), fp32 (before modulation)
+  uint16_t* d_table16;   // [C,H]  the same table in the tensor-core operand format (fp16 / bf16)
   float*    d_net_wT;    // [(L-1)][H(k)][H(n)]  fp32 transposed hidden weights (fp32 mode)
   uint16_t* d_net_w16;   // [(L-1)][H/8 (kc)][H (n)][8]  fp16/bf16 UMMA K-major no-swizzle operand layout
   uint16_t* d_net_w16p;  // [(L-1)][2 (rank)][H/8 (kc)][H/2 (n)][8]  same, split by output-row half for cta_group::2
@@ -83,6 +84,7 @@ int run_transpose(const float* w, int N, int K, float* wT, cudaStream_t st);
 int run_pack_w16(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_t st);
 int run_pack_w16_pair(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_t st);
 int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf16, uint16_t* out, cudaStream_t st);
+int run_table16(const float* table, long long n, int use_bf16, uint16_t* out, cudaStream_t st);
 int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,
                      int activation, float* table, cudaStream_t st);
 bool dense_split_supported(int N, int K1, int K2);

@@ -340,6 +340,24 @@ int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf1
   return check_launch("pack_w16_pair_bias");
 }
 
+__global__ void table16_kernel(const float* __restrict__ table, long long n, int use_bf16, uint16_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (use_bf16) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(table[i]);
+    out[i] = *reinterpret_cast<const uint16_t*>(&b);
+  } else {
+    const __half h = __float2half_rn(table[i]);
+    out[i] = *reinterpret_cast<const uint16_t*>(&h);
+  }
+}
+
+int run_table16(const float* table, long long n, int use_bf16, uint16_t* out, cudaStream_t st) {
+  table16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, n, use_bf16, out);
+  count_launch();
+  return check_launch("table16");
+}
+
 int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,
                      int activation, float* table, cudaStream_t st) {
   layer0_table_kernel<<<(C * H + 255) / 256, 256, 0, st>>>(grid, w, b, C, H, w0_initial, activation, table);

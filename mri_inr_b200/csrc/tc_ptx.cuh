@@ -200,6 +200,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_n(uint32_t bar, uint32_t cta, uint32_t count) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra], %2;\n\t}" ::"r"(bar), "r"(cta), "r"(count)
+      : "memory");
+}
 // (plain acquire.cta wait: an acquire at cluster scope would invalidate this SM's L1 on every probe)
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -311,6 +321,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 
 struct SirenTcParams {
   const float* table0;      // [C,256]
+  const uint16_t* table16;  // [C,256]  the same table rounded to the operand format (fp16 / bf16)
   const uint16_t* w16;      // [(L-1)][32][256][8]
   const uint16_t* w16p;     // [(L-1)][2][32][128][8]   (cta_group::2 path)
   const uint16_t* w16q;     // [(L-1)][2][34][128][8]   (cta_group::2 path, bias carried by a 17th K step)

@@ -79,16 +79,18 @@ __device__ __forceinline__ void small_dft(float2 (&v)[R], float sgn) {
 }
 
 // One Stockham pass of radix R over kG sequences of length n held in shared memory.
-// Element i of sequence g lives at x[g * ss + i * es]; COLS selects which index runs fastest across threads.
+// Element i of sequence g lives at x[g * ss + i * es].  Thread mapping without run-time divisions: for row
+// transforms a warp owns one sequence and its lanes stride over the butterflies; for column transforms the
+// sequence index is the fastest (kG is a power of two).  k = j mod Ns uses a mask while Ns is a power of two
+// (radices 4 and 2 come first in the plan), a modulo only in the trailing radix-3/5 stages.
 template <int R, bool COLS>
 __device__ __forceinline__ void stage(const float2* __restrict__ x, float2* __restrict__ y, int n, int Ns, int ss, int es,
                                       const float2* __restrict__ tw, float sgn) {
   const int nb = n / R;
   const int tstep = n / (Ns * R);
-  for (int w = threadIdx.x; w < nb * kG; w += kThreads) {
-    int g, j;
-    if (COLS) { g = w % kG; j = w / kG; } else { g = w / nb; j = w - g * nb; }
-    const int k = j % Ns;
+  const bool pow2 = (Ns & (Ns - 1)) == 0;
+  auto butterfly = [&](int g, int j) {
+    const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
     float2 v[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) {
@@ -99,6 +101,13 @@ __device__ __forceinline__ void stage(const float2* __restrict__ x, float2* __re
     const int j0 = (j - k) * R + k;
 #pragma unroll
     for (int q = 0; q < R; ++q) y[g * ss + (j0 + q * Ns) * es] = v[q];
+  };
+  if (COLS) {
+    for (int w = threadIdx.x; w < nb * kG; w += kThreads) butterfly(w & (kG - 1), w / kG);
+  } else {
+    static_assert(kThreads / 32 == kG, "one warp per sequence");
+    const int g = threadIdx.x >> 5;
+    for (int j = threadIdx.x & 31; j < nb; j += 32) butterfly(g, j);
   }
 }
 
@@ -142,8 +151,8 @@ rows_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmask, 
   build_twiddles(tw, n, sgn);
   const long long row0 = (long long)blockIdx.x * kG;
   const int half = n / 2;
-  for (int w = threadIdx.x; w < kG * n; w += kThreads) {
-    const int g = w / n, i = w - g * n;            // i = index in the source row (coalesced)
+  const int g = threadIdx.x >> 5;                  // one warp per row
+  for (int i = threadIdx.x & 31; i < n; i += 32) {   // i = index in the source row (coalesced)
     float2 v = make_float2(0.f, 0.f);
     if (row0 + g < n_rows) {
       v = __ldg(in + (row0 + g) * n + i);
@@ -156,14 +165,14 @@ rows_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmask, 
   }
   __syncthreads();
   const float2* r = run_stages<false>(a, b, plan, ss, 1, tw, sgn);
-  for (int w = threadIdx.x; w < kG * n; w += kThreads) {
-    const int g = w / n, o = w - g * n;            // o = index in the destination row (coalesced)
-    if (row0 + g >= n_rows) continue;
-    // fftshift: out[o] = r[(o - n/2) mod n]
-    int m = o - half;
-    if (m < 0) m += n;
-    const float2 v = r[g * ss + m];
-    out[(row0 + g) * n + o] = make_float2(v.x * scale, v.y * scale);
+  if (row0 + g < n_rows) {
+    for (int o = threadIdx.x & 31; o < n; o += 32) {   // o = index in the destination row (coalesced)
+      // fftshift: out[o] = r[(o - n/2) mod n]
+      int m = o - half;
+      if (m < 0) m += n;
+      const float2 v = r[g * ss + m];
+      out[(row0 + g) * n + o] = make_float2(v.x * scale, v.y * scale);
+    }
   }
 }
 
@@ -183,7 +192,7 @@ cols_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __
   const float2* src = in + img * (long long)H * W;
   const int half = n / 2;
   for (int w = threadIdx.x; w < kG * n; w += kThreads) {
-    const int g = w % kG, i = w / kG;              // g fastest: 64-byte row segments
+    const int g = w & (kG - 1), i = w / kG;        // g fastest: 64-byte row segments
     float2 v = make_float2(0.f, 0.f);
     if (x0 + g < W) v = __ldg(src + (long long)i * W + x0 + g);
     int m = i - half;
@@ -193,7 +202,7 @@ cols_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __
   __syncthreads();
   const float2* r = run_stages<true>(a, b, plan, 1, kG, tw, sgn);
   for (int w = threadIdx.x; w < kG * n; w += kThreads) {
-    const int g = w % kG, o = w / kG;
+    const int g = w & (kG - 1), o = w / kG;
     if (x0 + g >= W) continue;
     int m = o - half;
     if (m < 0) m += n;

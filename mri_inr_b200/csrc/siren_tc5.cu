@@ -255,7 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     };
     // this warp is done with the phase: its part of A[slot] is written (publish_a) and its modulation reads are over
     auto finish_phase = [&](int slot, uint32_t use, bool publish_a) {
-      fence_proxy_async();
+      if (publish_a) fence_proxy_async();        // generic-proxy writes of A -> visible to the tensor core's reads
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(kBarModEmpty + slot * kModStages + (int)(use & (kModStages - 1))));
@@ -312,6 +312,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       float* ring = mod_stage(slot, use);
 #pragma unroll
       for (int j = tid; j < kMaxSub * kH; j += kEpiWarps * 32) ring[j] *= w_mine;
+      // these generic-proxy writes must be ordered before the producer's next cp.async.bulk into this stage; fencing
+      // here (not at the end of the phase) hides the fence behind the barrier and the accumulator wait
+      fence_proxy_async();
       named_bar_sync(1, kEpiWarps * 32);
       const float* mp = ring + sub_prev * kH + cg * kCols;
       mbar_wait(bar(kBarAccFull + slot), ev & 1u, P.errflag, 5);

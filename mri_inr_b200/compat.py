@@ -37,7 +37,10 @@ def _ensure_package(name: str) -> types.ModuleType:
         return mod
 
 
-def install() -> None:
+def install(gpu_metrics: bool = False) -> None:
+    """``gpu_metrics=True`` additionally replaces ``src.util.error.metrics_error`` and the ``calculate_*`` helpers by
+    the device versions of :mod:`mri_inr_b200.error` (the reference's own module must then be importable, i.e.
+    scikit-image / matplotlib installed; its ``visual_error`` stays untouched)."""
     from . import modulated_siren, tiling
 
     for pkg in ("src", "src.networks", "src.util"):
@@ -46,6 +49,12 @@ def install() -> None:
     sys.modules["src.util.tiling"] = tiling
     setattr(sys.modules["src.networks"], "modulated_siren", modulated_siren)
     setattr(sys.modules["src.util"], "tiling", tiling)
+    if gpu_metrics:
+        from . import error as our_error
+
+        ref_error = importlib.import_module("src.util.error")
+        for name in our_error.__all__:
+            setattr(ref_error, name, getattr(our_error, name))
 
 
 def uninstall() -> None:

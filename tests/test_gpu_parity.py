@@ -482,6 +482,33 @@ def test_kernels_stay_inside_their_output_buffers():
     torch.cuda.synchronize()
 
 
+def test_metrics_error_mirror_matches_reference_flow():
+    """mri_inr_b200.error.metrics_error (same signature as src/util/error.py:200-271) against the oracle's restatement
+    of that flow: filter black -> model -> reintegrate -> weighted fold, unweighted fold of the fully sampled
+    patches, then PSNR / SSIM / NRMSE.  north_star: 0.05 dB / 1e-3."""
+    from mri_inr_b200 import error, tiling
+    from oracle import metrics as ometrics
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    full_img = synth_image(91, 96, 112)
+    under_img = (full_img * 0.7 + 0.1 * synth_image(92, 96, 112)).astype(np.float32)
+    under_img[:24, :28] = 0.0
+    fp, info = tiling.image_to_patches(torch.from_numpy(full_img)[None].to(DEV), 32, 16)
+    up, _ = tiling.image_to_patches(torch.from_numpy(under_img)[None].to(DEV), 32, 16)
+    got = error.metrics_error(m, fp, up, info, DEV, 32, 16, 24)
+    patches, oinfo = otiling.image_to_patches(under_img[None], 32, 16)
+    kept, black, shape = otiling.filter_and_remember_black_patches(patches)
+    out = osiren.model_forward(sd, torch.from_numpy(kept), activation=act).numpy()
+    rec = otiling.patches_to_image_weighted_average(otiling.reintegrate_black_patches(out, black, shape), oinfo, 24, 16)[0]
+    fpatches, _ = otiling.image_to_patches(full_img[None], 32, 16)
+    ref = otiling.patches_to_image(fpatches, oinfo, 32, 16)[0]
+    want = (ometrics.psnr(ref, rec), ometrics.ssim(ref, rec), ometrics.nrmse(ref, rec))
+    print("metrics_error:", got, "oracle:", want)
+    assert len(black) > 0
+    assert abs(got[0] - want[0]) <= 0.05 and abs(got[1] - want[1]) <= 1e-3 and abs(got[2] - want[2]) <= 1e-3
+
+
 def test_cpu_tensors_and_grad_are_refused():
     name, sd_kw, act, model_kw = MODEL_CASES[0]
     m, sd = _model(sd_kw, act, model_kw, "fp16")

@@ -72,3 +72,37 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert rc == -2
     assert lib.mrinr_image_to_patches(None, 0, 320, 320, 32, 16, None, None, None) == 0      # empty batch
     assert lib.mrinr_pack_weights(None, 0, None, None) == -1
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(lib):
+    """Encoder, k-space front end and metrics: sizing is host arithmetic; null / unsupported / undersized arguments are
+    rejected before any CUDA call; empty batches succeed."""
+    p = ctypes.c_void_p
+    # workspace sizing
+    assert lib.mrinr_encoder_workspace_bytes(0) == 0
+    assert lib.mrinr_encoder_workspace_bytes(94000) == 94000 * (2048 + 64) * 4
+    assert lib.mrinr_fft2c_workspace_bytes(3, 320, 320) == 3 * 320 * 320 * 8
+    assert lib.mrinr_image_metrics_scratch_bytes(10) >= 10 * 32
+    # empty batches are no-ops
+    assert lib.mrinr_encoder_forward(None, None, 0, None, None, 0, None) == 0
+    assert lib.mrinr_fft2c(None, 0, 320, 320, 1, None, None, 0, None) == 0
+    assert lib.mrinr_kspace_to_image(None, None, 0, 320, 320, None, None, 0, None) == 0
+    assert lib.mrinr_image_metrics(None, None, 0, 320, 320, None, None, 0, None) == 0
+    # null pointers
+    assert lib.mrinr_encoder_forward(None, None, 4, None, None, 0, None) == -1
+    assert lib.mrinr_fft2c(None, 1, 320, 320, 1, None, None, 0, None) == -1 and b"null" in lib.mrinr_last_error()
+    assert lib.mrinr_image_metrics(None, None, 2, 320, 320, None, None, 0, None) == -1
+    # undersized workspace / scratch
+    rc = lib.mrinr_fft2c(p(64), 1, 320, 320, 1, p(64), p(64), 16, None)
+    assert rc == -1 and b"workspace" in lib.mrinr_last_error()
+    rc = lib.mrinr_image_metrics(p(64), p(64), 2, 320, 320, p(64), p(64), 8, None)
+    assert rc == -1 and b"scratch" in lib.mrinr_last_error()
+    # images smaller than the 7x7 SSIM window
+    assert lib.mrinr_image_metrics(p(64), p(64), 1, 5, 320, p(64), p(64), 1 << 20, None) == -1
+    # misaligned buffers
+    rc = lib.mrinr_kspace_to_image(p(68), None, 1, 320, 320, p(64), p(64), 1 << 30, None)
+    assert rc == -3
+    # sizes with a prime factor other than 2, 3, 5 (or above 1024) are refused, not silently mis-transformed
+    rc = lib.mrinr_fft2c(p(64), 1, 14, 320, 1, p(64), p(64), 1 << 30, None)
+    assert rc == -2 and b"products of 2, 3 and 5" in lib.mrinr_last_error()
+    assert lib.mrinr_fft2c(p(64), 1, 2048, 320, 1, p(64), p(64), 1 << 30, None) == -2

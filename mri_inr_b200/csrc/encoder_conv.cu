@@ -4,10 +4,13 @@
 //     -> y [B,32,8,8]   (= the [B,2048] operand of Conv2d(32,64,8), which dense_tc.cu evaluates as a plain product)
 //
 // fp32 FFMA on the CUDA cores (664 kFLOP per patch, K = 9 and K = 144: too thin for the tensor core without an
-// im2col expansion).  Persistent CTAs of 256 threads, 4 patches per pass, 64 threads per patch:
-//   conv1: a thread owns 4 consecutive output columns x all 16 channels (64 accumulators, 27 input values),
-//   conv2: a thread owns 4 consecutive output columns x 8 channels (32 accumulators); per (ci, ky) it reads 9 input
-//          values and 3 x 8 weights (two broadcast LDS.128 per tap) for 96 FFMA.
+// im2col expansion).  Persistent CTAs of 256 threads, 8 patches per pass, ONE WARP PER PATCH (4 patches per CTA and two CTAs per SM
+// measured slower):
+//   conv1: a thread owns 4 consecutive output columns x all 16 channels (64 accumulators, 27 input values), twice,
+//   conv2: a thread owns 4 consecutive output columns x 16 channels (64 accumulators); per (ci, ky) it reads 9 input
+//          values and 3 x 16 weights (four broadcast LDS.128 per tap) for 192 FFMA -- 0.16 shared-memory
+//          instructions per FFMA (the first version, 4 x 8 outputs per thread, had 0.26 and was LSU-bound at 53 % of
+//          the FFMA peak).
 // Both convolutions keep their zero padding as a border in shared memory (only index -1 is ever touched: stride 2,
 // pad 1, even sizes).  Summation order: taps in (ci, ky, kx) order, bias added last -- the result agrees with
 // cuDNN / the CPU reference to ~1e-6.
@@ -16,8 +19,8 @@
 namespace mrinr {
 namespace enc {
 
-constexpr int kP = 4;             // patches per pass
-constexpr int kThreads = 64 * kP;
+constexpr int kP = 8;             // patches per pass (one warp each)
+constexpr int kThreads = 32 * kP;
 constexpr int kInLd = 36;         // input tile [33][36]: row / col index + 1 (border at 0)
 constexpr int kInSz = 33 * kInLd;
 constexpr int kC1Ld = 18;         // conv1 map [17][18] per channel
@@ -35,7 +38,7 @@ struct Smem {
 
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : x * kSlope; }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 encoder_conv_kernel(const float* __restrict__ patches, long long B, const float* __restrict__ w1, const float* __restrict__ b1,
                     const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -53,14 +56,14 @@ encoder_conv_kernel(const float* __restrict__ patches, long long B, const float*
   for (int i = tid; i < kP * 16 * kC1Sz; i += kThreads) (&S.c1[0][0][0])[i] = 0.f;
   __syncthreads();
 
-  const int p = tid >> 6;          // patch slot of this thread
-  const int g = tid & 63;
+  const int p = tid >> 5;          // patch slot of this warp
+  const int lane = tid & 31;
   const long long n_groups = (B + kP - 1) / kP;
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long b0 = grp * kP;
     // ---- stage kP input patches (coalesced 16-byte loads) ----
 #pragma unroll
-    for (int i = 0; i < kP; ++i) {
+    for (int i = 0; i < kP * 1024 / (kThreads * 4); ++i) {
       const int e = (i * kThreads + tid) * 4;                // element index within the kP x 1024 block
       const int pp = e >> 10, r = (e >> 5) & 31, c = e & 31;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -69,8 +72,10 @@ encoder_conv_kernel(const float* __restrict__ patches, long long B, const float*
       dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
     __syncthreads();
-    // ---- conv1 + LeakyReLU: thread -> output row y, columns x0..x0+3, all 16 channels ----
-    {
+    // ---- conv1 + LeakyReLU: thread -> output row y, columns x0..x0+3, all 16 channels; two position groups ----
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int g = half * 32 + lane;
       const int y = g >> 2, x0 = (g & 3) * 4;
       float acc[4][16];
 #pragma unroll
@@ -102,18 +107,17 @@ encoder_conv_kernel(const float* __restrict__ patches, long long B, const float*
 #pragma unroll
         for (int j = 0; j < 4; ++j) S.c1[p][c][(y + 1) * kC1Ld + x0 + j + 1] = lrelu(acc[j][c] + S.b1[c]);
     }
-    __syncthreads();
-    // ---- conv2 + LeakyReLU: thread -> output row y, columns x0..x0+3, channels co0..co0+7 ----
+    __syncwarp();        // a patch's conv1 map is produced and consumed by the same warp
+    // ---- conv2 + LeakyReLU: thread -> output row y, columns x0..x0+3, channels co0..co0+15 ----
     {
-      const int lane = g & 31, wv = g >> 5;
-      const int co0 = (wv * 2 + (lane >> 4)) * 8;
+      const int co0 = (lane >> 4) * 16;
       const int y = lane & 7, x0 = ((lane >> 3) & 1) * 4;
-      float acc[4][8];
+      float acc[4][16];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
-#pragma unroll 2
+        for (int c = 0; c < 16; ++c) acc[j][c] = 0.f;
+#pragma unroll 1
       for (int ci = 0; ci < 16; ++ci) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -124,20 +128,23 @@ encoder_conv_kernel(const float* __restrict__ patches, long long B, const float*
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const float* wp = &S.w2[((ci * 3 + ky) * 3 + kx) * 32 + co0];
-            const float4 wa = *reinterpret_cast<const float4*>(wp);
-            const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
-            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            float w[16];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 t = *reinterpret_cast<const float4*>(wp + c4 * 4);
+              w[c4 * 4] = t.x; w[c4 * 4 + 1] = t.y; w[c4 * 4 + 2] = t.z; w[c4 * 4 + 3] = t.w;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-              for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(v[2 * j + kx], w[c], acc[j][c]);
+              for (int c = 0; c < 16; ++c) acc[j][c] = fmaf(v[2 * j + kx], w[c], acc[j][c]);
           }
         }
       }
       if (b0 + p < B) {
         float* dst = out + (b0 + p) * 2048 + y * 8 + x0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 16; ++c) {
           const float bb = S.b2[co0 + c];
           *reinterpret_cast<float4*>(dst + (co0 + c) * 64) =
               make_float4(lrelu(acc[0][c] + bb), lrelu(acc[1][c] + bb), lrelu(acc[2][c] + bb), lrelu(acc[3][c] + bb));
@@ -159,7 +166,7 @@ int launch_encoder_conv(const float* d_patches, long long B, const float* w1, co
     configured = true;
   }
   if (B <= 0) return 0;
-  long long grid = (long long)num_sms * 2;
+  long long grid = (long long)num_sms;
   const long long groups = (B + enc::kP - 1) / enc::kP;
   if (grid > groups) grid = groups;
   enc::encoder_conv_kernel<<<(unsigned)grid, enc::kThreads, smem, st>>>(d_patches, B, w1, b1, w2, b2, d_out);

@@ -22,6 +22,10 @@ namespace v4 {
 int launch_siren_tc_v4(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
                        int64_t B, float* d_out, cudaStream_t st);
 }
+namespace v7 {
+int launch_siren_tc_v7(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
+                       int64_t B, float* d_out, cudaStream_t st);
+}
 namespace v6 {
 int launch_siren_tc_v6(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
                        int64_t B, float* d_out, cudaStream_t st);
@@ -36,12 +40,13 @@ int launch_siren_tc(const MrinrPacked* p, const float* d_mods, const int32_t* d_
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("MRINR_TC_VARIANT");
-    variant = (e && e[0] >= '1' && e[0] <= '6') ? (e[0] - '0') : 5;
+    variant = (e && e[0] >= '1' && e[0] <= '7') ? (e[0] - '0') : 5;
   }
   if (variant == 1 || p->L < 3) return v1::launch_siren_tc_v1(p, d_mods, d_idx, d_nactive, B, d_out, st);
   if (variant == 2) return v2::launch_siren_tc_v2(p, d_mods, d_idx, d_nactive, B, d_out, st);
   if (variant == 3) return v3::launch_siren_tc_v3(p, d_mods, d_idx, d_nactive, B, d_out, st);
   if (variant == 4) return v4::launch_siren_tc_v4(p, d_mods, d_idx, d_nactive, B, d_out, st);
+  if (variant == 7) return v7::launch_siren_tc_v7(p, d_mods, d_idx, d_nactive, B, d_out, st);
   if (variant == 5) return v5::launch_siren_tc_v5(p, d_mods, d_idx, d_nactive, B, d_out, st);
   return v6::launch_siren_tc_v6(p, d_mods, d_idx, d_nactive, B, d_out, st);
 }

@@ -577,7 +577,7 @@ def test_psnr_ssim_within_north_star_tolerance():
         assert abs(got[i, 2] - metrics.nrmse(ref_img, want)) <= 1e-3
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "6"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "6", "7"])
 def test_earlier_kernel_variants_still_agree(variant):
     """The single-CTA kernels (v1, v2) and the chunk-chasing pair kernel (v3) are kept for A/B measurements; they must
     stay correct.  The variant is latched per process, so run them in a subprocess."""

@@ -77,77 +77,82 @@ encoder_conv_kernel(const float* __restrict__ patches, long long B, const float*
     for (int half = 0; half < 2; ++half) {
       const int g = half * 32 + lane;
       const int y = g >> 2, x0 = (g & 3) * 4;
-      float acc[4][16];
+      float2 acc[4][8];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[j][c] = 0.f;
+        for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const float* row = &S.in[p][(2 * y + ky) * kInLd + 2 * x0];       // input row 2y+ky-1, col 2x0-1 (border + 1)
-        float v[9];
+        float2 v[9];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) v[j] = row[j];
+        for (int j = 0; j < 9; ++j) v[j] = make_float2(row[j], row[j]);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          float w[16];
+          float2 w[8];
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const float4 t = *reinterpret_cast<const float4*>(&S.w1[(ky * 3 + kx) * 16 + c4 * 4]);
-            w[c4 * 4] = t.x; w[c4 * 4 + 1] = t.y; w[c4 * 4 + 2] = t.z; w[c4 * 4 + 3] = t.w;
+            w[c4 * 2] = make_float2(t.x, t.y); w[c4 * 2 + 1] = make_float2(t.z, t.w);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[j][c] = fmaf(v[2 * j + kx], w[c], acc[j][c]);
+            for (int c = 0; c < 8; ++c) acc[j][c] = __ffma2_rn(v[2 * j + kx], w[c], acc[j][c]);
         }
       }
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
+      for (int c = 0; c < 8; ++c)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) S.c1[p][c][(y + 1) * kC1Ld + x0 + j + 1] = lrelu(acc[j][c] + S.b1[c]);
+        for (int j = 0; j < 4; ++j) {
+          S.c1[p][2 * c][(y + 1) * kC1Ld + x0 + j + 1] = lrelu(acc[j][c].x + S.b1[2 * c]);
+          S.c1[p][2 * c + 1][(y + 1) * kC1Ld + x0 + j + 1] = lrelu(acc[j][c].y + S.b1[2 * c + 1]);
+        }
     }
     __syncwarp();        // a patch's conv1 map is produced and consumed by the same warp
     // ---- conv2 + LeakyReLU: thread -> output row y, columns x0..x0+3, channels co0..co0+15 ----
     {
       const int co0 = (lane >> 4) * 16;
       const int y = lane & 7, x0 = ((lane >> 3) & 1) * 4;
-      float acc[4][16];
+      float2 acc[4][8];              // [output column][channel pair]: one fma.rn.f32x2 per pair (same rounding as fmaf)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[j][c] = 0.f;
+        for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int ci = 0; ci < 16; ++ci) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const float* row = &S.c1[p][ci][(2 * y + ky) * kC1Ld + 2 * x0];
-          float v[9];
+          float2 v[9];
 #pragma unroll
-          for (int j = 0; j < 9; ++j) v[j] = row[j];
+          for (int j = 0; j < 9; ++j) v[j] = make_float2(row[j], row[j]);
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const float* wp = &S.w2[((ci * 3 + ky) * 3 + kx) * 32 + co0];
-            float w[16];
+            float2 w[8];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const float4 t = *reinterpret_cast<const float4*>(wp + c4 * 4);
-              w[c4 * 4] = t.x; w[c4 * 4 + 1] = t.y; w[c4 * 4 + 2] = t.z; w[c4 * 4 + 3] = t.w;
+              w[c4 * 2] = make_float2(t.x, t.y); w[c4 * 2 + 1] = make_float2(t.z, t.w);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-              for (int c = 0; c < 16; ++c) acc[j][c] = fmaf(v[2 * j + kx], w[c], acc[j][c]);
+              for (int c = 0; c < 8; ++c) acc[j][c] = __ffma2_rn(v[2 * j + kx], w[c], acc[j][c]);
           }
         }
       }
       if (b0 + p < B) {
         float* dst = out + (b0 + p) * 2048 + y * 8 + x0;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float bb = S.b2[co0 + c];
-          *reinterpret_cast<float4*>(dst + (co0 + c) * 64) =
-              make_float4(lrelu(acc[0][c] + bb), lrelu(acc[1][c] + bb), lrelu(acc[2][c] + bb), lrelu(acc[3][c] + bb));
+        for (int c = 0; c < 8; ++c) {
+          const float ba = S.b2[co0 + 2 * c], bb = S.b2[co0 + 2 * c + 1];
+          *reinterpret_cast<float4*>(dst + (co0 + 2 * c) * 64) = make_float4(
+              lrelu(acc[0][c].x + ba), lrelu(acc[1][c].x + ba), lrelu(acc[2][c].x + ba), lrelu(acc[3][c].x + ba));
+          *reinterpret_cast<float4*>(dst + (co0 + 2 * c + 1) * 64) = make_float4(
+              lrelu(acc[0][c].y + bb), lrelu(acc[1][c].y + bb), lrelu(acc[2][c].y + bb), lrelu(acc[3][c].y + bb));
         }
       }
     }

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -317,7 +318,17 @@ extern "C" int mrinr_encoder_forward(const MrinrPacked* p, const float* d_patche
   cudaStream_t st = (cudaStream_t)stream;
   float* c2 = static_cast<float*>(d_workspace);
   float* c3 = c2 + (size_t)B * 2048;
-  int rc = launch_encoder_conv(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms, st);
+  // conv1 + conv2: tensor-core implicit GEMM for conv2 (encoder_conv_tc.cu) unless MRINR_ENC_VARIANT=ffma selects the
+  // all-FFMA kernel (encoder_conv.cu), kept for A/B measurements
+  static int enc_variant = -1;
+  if (enc_variant < 0) {
+    const char* e = getenv("MRINR_ENC_VARIANT");
+    enc_variant = (e && e[0] == 'f') ? 0 : 1;
+  }
+  int rc = enc_variant
+               ? launch_encoder_conv_tc(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms,
+                                        p->d_errflag, st)
+               : launch_encoder_conv(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms, st);
   if (rc != 0) return rc;
   // Conv2d(32,64,8) on the 8x8 map == [B,2048] x [2048,64] (weight [64,32,8,8] flattens in the same (c,y,x) order)
   rc = launch_dense_split(c2, 2048, 2048, nullptr, 0, 0, p->d_enc_w3s, p->d_enc_b3, 64, /*leaky*/ 2, 0.2f, c3, 64, B,

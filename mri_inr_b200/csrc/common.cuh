@@ -94,6 +94,8 @@ int launch_dense_split(const float* a1, long long lda1, int K1, const float* a2,
                        long long ldc, long long M, int32_t* errflag, cudaStream_t st);
 int launch_encoder_conv(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,
                         const float* b2, float* d_out, int num_sms, cudaStream_t st);
+int launch_encoder_conv_tc(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,
+                           const float* b2, float* d_out, int num_sms, int32_t* errflag, cudaStream_t st);
 int launch_compact_black(const uint8_t* d_black, int64_t B, int32_t C, int32_t* d_idx, int32_t* d_nactive,
                          int32_t* d_blocksums, float* d_out, cudaStream_t st);
 

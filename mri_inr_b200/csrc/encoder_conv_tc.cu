@@ -36,14 +36,18 @@ namespace mrinr {
 namespace enctc {
 
 #ifndef MRINR_ENC_GROUPS
-#define MRINR_ENC_GROUPS 2
+#define MRINR_ENC_GROUPS 3
 #endif
 constexpr int kGroups = MRINR_ENC_GROUPS;
 constexpr int kGroupThreads = 128;
 constexpr int kWarpMma = kGroups * 4;
 constexpr int kThreads = kGroups * kGroupThreads + 32;
-constexpr int kInLd = 36;                    // input tile [33][36]: row / col index + 1 (zero border at 0)
+// input tile: image row r-1 / column c-4 at [r * kInLd + skew(r) + c]; row 0 and column index 3 are the zero border.
+// Column offset 4 keeps both the staging stores and conv1's loads (index 8q+3 | 8q+4..7 | 8q+8..11) 16-byte
+// aligned; the 4-float skew of every other row pair puts the two rows of a quarter-warp on disjoint banks.
+constexpr int kInLd = 40;
 constexpr int kInSz = 33 * kInLd;
+__device__ __forceinline__ int in_row(int r) { return r * kInLd + ((r >> 1) & 1) * 4; }
 constexpr float kSlope = 0.2f;
 
 constexpr int kRowBytes = 17 * 16;                     // 9 odd-column entries + 8 even-column entries
@@ -60,7 +64,7 @@ static_assert(kChunkBytes % 16 == 0, "descriptor strides are in 16-byte units");
 constexpr int kOffMap = 0;
 constexpr int kOffW = kOffMap + kGroups * kMapBytes;
 constexpr int kOffIn = kOffW + 2 * kWHalfBytes;
-constexpr int kOffW1 = kOffIn + kGroups * 2 * kInSz * 4;     // [ky][kx][co] f32
+constexpr int kOffW1 = kOffIn + kGroups * 2 * 2 * kInSz * 4; // input tiles: [group][buffer][patch]; then [ky][kx][co] f32
 constexpr int kOffB1 = kOffW1 + 9 * 16 * 4;
 constexpr int kOffB2 = kOffB1 + 16 * 4;
 constexpr int kOffBar = kOffB2 + 32 * 4;
@@ -104,7 +108,7 @@ encoder_conv_tc_kernel(const float* __restrict__ patches, long long B, const flo
 
   // ---- once per CTA: zero the maps (their border lines stay zero) and the input tiles, split the conv2 weights ----
   for (int i = tid; i < (kOffW - kOffMap) / 16; i += kThreads) reinterpret_cast<uint4*>(smem + kOffMap)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < kGroups * 2 * kInSz; i += kThreads) reinterpret_cast<float*>(smem + kOffIn)[i] = 0.f;
+  for (int i = tid; i < kGroups * 4 * kInSz; i += kThreads) reinterpret_cast<float*>(smem + kOffIn)[i] = 0.f;
   for (int i = tid; i < 9 * 16 * 32; i += kThreads) {
     const int co = i & 31, ci = (i >> 5) & 15, tap = i >> 9;
     const float x = w2[(co * 16 + ci) * 9 + tap];                    // Conv2d weight [co][ci][ky][kx]
@@ -132,7 +136,7 @@ encoder_conv_tc_kernel(const float* __restrict__ patches, long long B, const flo
   if (warp < kWarpMma) {
     // =========================== worker warpgroups ===========================
     const int grp = warp >> 2, wg = warp & 3, gt = tid & (kGroupThreads - 1);
-    float* s_in = reinterpret_cast<float*>(smem + kOffIn) + grp * 2 * kInSz;
+    float* s_in0 = reinterpret_cast<float*>(smem + kOffIn) + grp * 4 * kInSz;
     uint8_t* map = smem + kOffMap + grp * kMapBytes;
     // conv1 role: patch pp of the pair, rows y (0..15), columns x0..x0+3, all 16 channels
     const int pp = wg >> 1;
@@ -144,33 +148,54 @@ encoder_conv_tc_kernel(const float* __restrict__ patches, long long B, const flo
     const uint32_t taddr = tmem_base + (uint32_t)(grp * 32) + ((uint32_t)(wg * 32) << 16);
     uint32_t it = 0;
     long long prev_pair = -1;
+    // the pair's 2 x 1024 inputs are fetched one iteration ahead (coalesced 16-byte loads, 4 per thread), so that the
+    // global-memory latency hides behind the previous pair's arithmetic; a missing second patch is staged as zeros
+    constexpr int kLd = 2 * 1024 / (kGroupThreads * 4);
+    float4 nxt[kLd];
+    auto fetch = [&](long long pair) {
+#pragma unroll
+      for (int i = 0; i < kLd; ++i) {
+        const int e = (i * kGroupThreads + gt) * 4;
+        const long long b = 2 * pair + (e >> 10);
+        nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < B) nxt[i] = __ldg(reinterpret_cast<const float4*>(patches + b * 1024 + (e & 1023)));
+      }
+    };
+    if (blockIdx.x + (long long)grp * gridDim.x < n_pairs) fetch(blockIdx.x + (long long)grp * gridDim.x);
     for (long long k = grp;; k += kGroups) {
       const long long pair = blockIdx.x + k * (long long)gridDim.x;
       const bool active = pair < n_pairs;
       float2 acc[4][8];
+      // input tiles are double-buffered: the barrier after the staging of iteration i also orders every warp's conv1
+      // reads of iteration i-1 before the staging of iteration i+1 (same buffer as i-1)
+      float* s_in = s_in0 + (it & 1u) * 2 * kInSz;
       if (active) {
-        // ---- stage the two patches (coalesced 16-byte loads; a missing second patch is staged as zeros) ----
+        // ---- stage the two patches ----
 #pragma unroll
-        for (int i = 0; i < 2 * 1024 / (kGroupThreads * 4); ++i) {
+        for (int i = 0; i < kLd; ++i) {
           const int e = (i * kGroupThreads + gt) * 4;
           const int sp = e >> 10, r = (e >> 5) & 31, c = e & 31;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (2 * pair + sp < B) v = __ldg(reinterpret_cast<const float4*>(patches + (2 * pair + sp) * 1024 + r * 32 + c));
-          float* dst = s_in + sp * kInSz + (r + 1) * kInLd + c + 1;
-          dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+          *reinterpret_cast<float4*>(s_in + sp * kInSz + in_row(r + 1) + c + 4) = nxt[i];
         }
+        const long long pair_next = pair + (long long)kGroups * gridDim.x;
+        if (pair_next < n_pairs) fetch(pair_next);
         named_bar_sync(1 + grp, kGroupThreads);
         // ---- conv1: taps in (ky, kx) order, packed fma.rn.f32x2 over channel pairs ----
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < 8; ++c) {
+          const float2 bb = *reinterpret_cast<const float2*>(&s_b1[2 * c]);     // accumulators start at the bias
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(0.f, 0.f);
+          for (int j = 0; j < 4; ++j) acc[j][c] = bb;
+        }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const float* row = s_in + pp * kInSz + (2 * y + ky) * kInLd + 2 * x0;   // input row 2y+ky-1, col 2x0-1
-          float2 v[9];
-#pragma unroll
-          for (int j = 0; j < 9; ++j) v[j] = make_float2(row[j], row[j]);
+          const float* row = s_in + pp * kInSz + in_row(2 * y + ky) + 2 * x0 + 3;   // input row 2y+ky-1, col 2x0-1
+          const float r0 = row[0];
+          const float4 r1 = *reinterpret_cast<const float4*>(row + 1);
+          const float4 r2 = *reinterpret_cast<const float4*>(row + 5);
+          const float2 v[9] = {make_float2(r0, r0),     make_float2(r1.x, r1.x), make_float2(r1.y, r1.y),
+                               make_float2(r1.z, r1.z), make_float2(r1.w, r1.w), make_float2(r2.x, r2.x),
+                               make_float2(r2.y, r2.y), make_float2(r2.z, r2.z), make_float2(r2.w, r2.w)};
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             float2 w[8];
@@ -190,16 +215,26 @@ encoder_conv_tc_kernel(const float* __restrict__ patches, long long B, const flo
         // ---- epilogue of the group's previous pair: its MMAs ran underneath the staging and conv1 above ----
         mbar_wait(bar_acc(grp), (it - 1u) & 1u, errflag, 31);
         tc_fence_after();
-        uint32_t d[32];
-        tmem_ld32(taddr, d);
-        tmem_ld_wait();
-        tc_fence_before();
         const long long b = 2 * prev_pair + pe;
-        if (b < B) {
-          float* dst = out + b * 2048 + ye * 8 + xe;
+        float* dst = out + b * 2048 + ye * 8 + xe;
 #pragma unroll
-          for (int co = 0; co < 32; ++co) dst[co * 64] = lrelu(__uint_as_float(d[co]) + s_b2[co]);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t d[16];
+          tmem_ld16(taddr + (uint32_t)(h * 16), d);
+          tmem_ld_wait();
+          if (b < B) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 bb = *reinterpret_cast<const float4*>(&s_b2[h * 16 + c4 * 4]);
+              float* o = dst + (h * 16 + c4 * 4) * 64;
+              o[0] = lrelu(__uint_as_float(d[c4 * 4]) + bb.x);
+              o[64] = lrelu(__uint_as_float(d[c4 * 4 + 1]) + bb.y);
+              o[128] = lrelu(__uint_as_float(d[c4 * 4 + 2]) + bb.z);
+              o[192] = lrelu(__uint_as_float(d[c4 * 4 + 3]) + bb.w);
+            }
+          }
         }
+        tc_fence_before();
       }
       if (!active) break;
       // ---- bias + LeakyReLU + split, written in the tap-addressable layout (see the header) ----
@@ -215,8 +250,10 @@ encoder_conv_tc_kernel(const float* __restrict__ patches, long long B, const flo
             float v[8];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              v[2 * c] = lrelu(acc[j][c2 * 4 + c].x + s_b1[c2 * 8 + 2 * c]);
-              v[2 * c + 1] = lrelu(acc[j][c2 * 4 + c].y + s_b1[c2 * 8 + 2 * c + 1]);
+              const float2 a = acc[j][c2 * 4 + c];
+              const float2 sl = __fmul2_rn(a, make_float2(kSlope, kSlope));
+              v[2 * c] = fmaxf(a.x, sl.x);
+              v[2 * c + 1] = fmaxf(a.y, sl.y);
             }
             uint4 hi, lo;
             split8(v, hi, lo);
@@ -229,7 +266,6 @@ encoder_conv_tc_kernel(const float* __restrict__ patches, long long B, const flo
       fence_proxy_async();             // generic-proxy writes of the map -> visible to the tensor core's reads
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_afull(grp));
-      named_bar_sync(1 + grp, kGroupThreads);      // every warp is done with the input tiles before the next staging
       prev_pair = pair;
       ++it;
     }

@@ -94,6 +94,21 @@ __device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& 
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+__device__ __forceinline__ void split4(const float4& u, uint2& hi, uint2& lo) {
+  const float x[4] = {u.x, u.y, u.z, u.w};
+  uint32_t h[2], l[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint2(h[0], h[1]);
+  lo = make_uint2(l[0], l[1]);
+}
+
 template <int N>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) dense_split_kernel(const DenseParams P) {
   using C = Cfg<N>;
@@ -134,25 +149,35 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
     // =========================== A producers, then epilogue ===========================
     const long long row = (long long)blockIdx.x * kBM + tid;
     const bool live = row < P.M;
+    // Loads are COALESCED: one warp instruction covers 4 rows x 128 bytes (lane -> row 4i + lane/8, floats 4 (lane%8)
+    // .. +3 of the slab) instead of 32 different lines (thread = row), which kept the L1 tag stage busy 8x longer for
+    // the same bytes.  A lane then owns half of a 16-byte UMMA entry (4 of its 8 K values) and stores 8 bytes.
+    const int lrow = lane >> 3, lq = lane & 7;
+    const long long row0 = (long long)blockIdx.x * kBM + warp * 32 + lrow;      // + 4 i
     auto load_slab = [&](int slab, float4 (&r)[2 * kKc]) {
       const int k = slab * kSlabK;
-      const float* src = (k < P.K1) ? P.a1 + row * P.lda1 + k : P.a2 + row * P.lda2 + (k - P.K1);
+      const float* src = (k < P.K1) ? P.a1 + row0 * P.lda1 + k : P.a2 + row0 * P.lda2 + (k - P.K1);
+      const long long ld = (k < P.K1) ? P.lda1 : P.lda2;
 #pragma unroll
-      for (int i = 0; i < 2 * kKc; ++i) r[i] = live ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 2 * kKc; ++i)
+        r[i] = (row0 + 4 * i < P.M) ? __ldg(reinterpret_cast<const float4*>(src + (long long)(4 * i) * ld) + lq)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    static_assert(kSlabK == 32 && 2 * kKc == 8, "a warp instruction covers 4 rows of one 32-column slab");
     float4 r[2 * kKc];
     if (n_slabs > 0) load_slab(0, r);
+    const int st_off = (lq >> 1) * (kBM * 16) + (warp * 32 + lrow) * 16 + (lq & 1) * 8;    // + 64 i
     for (int slab = 0; slab < n_slabs; ++slab) {
       const int st = slab % kStages;
       mbar_wait(bar_empty(st), ((slab / kStages) & 1u) ^ 1u, P.errflag, 21);
-      uint8_t* a_hi = smem + st * C::kStageBytes;
+      uint8_t* a_hi = smem + st * C::kStageBytes + st_off;
       uint8_t* a_lo = a_hi + kAHalfBytes;
 #pragma unroll
-      for (int kc = 0; kc < kKc; ++kc) {
-        uint4 hi, lo;
-        split8(r[2 * kc], r[2 * kc + 1], hi, lo);
-        *reinterpret_cast<uint4*>(a_hi + kc * (kBM * 16) + tid * 16) = hi;
-        *reinterpret_cast<uint4*>(a_lo + kc * (kBM * 16) + tid * 16) = lo;
+      for (int i = 0; i < 2 * kKc; ++i) {
+        uint2 hi, lo;
+        split4(r[i], hi, lo);
+        *reinterpret_cast<uint2*>(a_hi + i * 64) = hi;
+        *reinterpret_cast<uint2*>(a_lo + i * 64) = lo;
       }
       if (slab + 1 < n_slabs) load_slab(slab + 1, r);      // in flight while the tensor core works on this slab
       fence_proxy_async();

@@ -38,6 +38,16 @@ __global__ void bench(float* out, int iters, long long* cycles, const float4* gs
         if (MODE == 6) { uint32_t v[16]; tmem_ld16(tm + ((i * 16 + k * 64) & 255), v); tmem_ld_wait(); y[(i + k) & 7] += __uint_as_float(v[0]) * 0.f; }
         if (MODE == 4) asm volatile("mul.rz.f32 %0, %0, %1;" : "+f"(y[(i + k) & 7]) : "f"(1.0001f));
       }
+      // MODE 7: the synthesis epilogue's mix per 8 sines: 8 FMUL + 4 F2FP, and K STS.128 per 16 sines (K = 0, 1, 2, 4)
+      if (MODE == 7) {
+        asm volatile("mul.f32 %0, %0, %1;" : "+f"(y[i]) : "f"(1.0001f));
+        if (i & 1) { unsigned r; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y[i]), "f"(y[i - 1])); y[i] = __uint_as_float(r | 0x3f000000u); }
+      }
+      if (MODE == 7 && K >= 1 && i == 7 && ((it & 1) || K >= 2)) {
+        const int n = K >= 2 ? K / 2 : 1;
+        for (int q = 0; q < n; ++q)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" :: "r"((unsigned)__cvta_generic_to_shared(&sbuf[(threadIdx.x + q * 256) & 1023])), "f"(y[q & 7]) : "memory");
+      }
     }
   }
   const long long t1 = clock64();
@@ -58,7 +68,7 @@ void run(int warps_per_smsp, float* d_out, long long* d_cyc) {
   long long c;
   cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost);
   // per SMSP: warps_per_smsp warps x iters x 8 groups of (1 MUFU(+FMUL.RZ) + K FFMA)
-  const char* names[] = {"FFMA", "F2FP", "STS.128", "LDS.128", "FMUL.RZ", "LDG.128u", "LDTM.x16"};
+  const char* names[] = {"FFMA", "F2FP", "STS.128", "LDS.128", "FMUL.RZ", "LDG.128u", "LDTM.x16", "STS.128 per 16 sines (epilogue mix)"};
   printf("warps/SMSP %d, %2d %-8s per MUFU.SIN: %.2f cycles per group per SMSP\n", warps_per_smsp, K, names[MODE],
          (double)c / (iters * 8.0 * warps_per_smsp));
 }
@@ -74,6 +84,7 @@ int main() {
     run<2, 4>(w, d_out, d_cyc); run<4, 4>(w, d_out, d_cyc);
     run<1, 5>(w, d_out, d_cyc); run<2, 5>(w, d_out, d_cyc);
     run<1, 6>(w, d_out, d_cyc);
+    run<0, 7>(w, d_out, d_cyc); run<1, 7>(w, d_out, d_cyc); run<2, 7>(w, d_out, d_cyc); run<4, 7>(w, d_out, d_cyc);
   }
   return 0;
 }

@@ -41,7 +41,12 @@ constexpr int kEpiWarps = MRINR_V5_EPI_WARPS;  // 8 or 16: 2 or 4 epilogue warps
 constexpr int kColGroups = kEpiWarps / 4;      // a warp owns rows 32(w&3)..+31 and columns [kCols*(w>>2), +kCols)
 constexpr int kCols = 256 / kColGroups;        // 128 or 64 columns per thread per phase
 constexpr int kPairs = kCols / 32;             // pairs of 16-column chunks per phase
-constexpr int kThreads = kEpiWarps * 32 + 64;
+constexpr int kThreads = kEpiWarps * 32 + 128;  // + one warpgroup: MMA issuer, producer, two idle warps
+// setmaxnreg works on whole warpgroups: the epilogue warpgroups grow to kRegsEpilogue registers and the helper
+// warpgroup shrinks to kRegsOther (per sub-partition: 2 x 232 + 40 <= 512).  At the launch cap of 168 the compiler
+// spilled the tile-walk state, and with 226 KB of shared memory there is next to no L1 left: every reload was an
+// L2 round trip (~300 cycles) on the critical path between phases (tools/timeline.py).
+constexpr int kRegsEpilogue = kEpiWarps == 8 ? 232 : 112, kRegsOther = 40;
 // Register budget: the register file is split per SM sub-partition (16 384 each) and the 10 (18) warps of the CTA
 // land 3 (5) on some sub-partition, so the cap is 168 (96) registers per thread -- not 65536 / kThreads.
 constexpr int kMaxLayers = 16;
@@ -223,6 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 
   if (warp < kEpiWarps) {
     // =========================== epilogue warps (both CTAs, identical) ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     const int q = warp & 3;
     const int cg = warp >> 2;          // column group
     const int t = q * 32 + lane;       // tile row == TMEM lane
@@ -353,6 +359,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         if (hp < kPairs - 1) tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
         dot16(vb, hp * 2 + 1);
       }
+      TL(1020 + slot);
       tc_fence_before();
       finish_phase(slot, use, false);
       float dot = (d0 + d1) + (d2 + d3);
@@ -368,6 +375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         // output layer: always sine, never modulated (modulated_siren.py:211-213, :233)
         if (outp != nullptr) *outp = sin_accurate(P.w0 * (dot + last_b));
       }
+      TL(1030 + slot);
     };
 
     Walk w;
@@ -401,7 +409,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       // ---- per slot: finish the previous tile of the slot, then write the layer-0 operand of the new one ----
 #pragma unroll 1
       for (int slot = 0; slot < 2; ++slot) {
+        TL(910 + slot);
         const uint32_t ok0 = last ? 1u : peek_mods(slot, use0);
+        TL(920 + slot);
         if (it > 0) final_phase(slot, slot ? out1 : out0, ev0 - 1u, use0 - 1u);
         if (last) continue;
         {
@@ -476,9 +486,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           TL(5000 + l * 10 + slot);
         }
       }
+      TL(900);
       w.next(S);
+      TL(901);
     }
   } else if (warp == kEpiWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     if (rank == 0) {
       // =========================== MMA issuer (leader CTA) ===========================
       // The whole warp runs the loop converged; one elected lane issues the tcgen05 instructions, so that all
@@ -491,7 +504,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       uint32_t ev = 0;
       for (long long it = 0; it < S.total; ++it) {
         for (int l = 1; l < L; ++l, ++ev) {
-#pragma unroll
+          // not unrolled over the slots: the issuer shares its sub-partition's instruction cache with two epilogue
+          // warps, and 12 KB of straight-line issue code evicted their loops at every phase change
+#pragma unroll 1
           for (int slot = 0; slot < 2; ++slot) {
             const uint32_t a_lo = a_lo0 + (uint32_t)slot * (65536u >> 4);
             const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
@@ -515,11 +530,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
                 } else {
                   umma_f16_pair_lohi(d_tmem, ones_lo, b_lo, desc_hi, idesc, 1u);      // + bias
                 }
-                if (slot == 1 && s == kNumSlabs - 1) {
-                  // both slots have consumed this layer's slabs: hand all of them back with one commit each
-#pragma unroll
-                  for (int r = 0; r < kNumSlabs; ++r) umma_commit_pair(bar(kBarWEmpty + r), 3);
-                }
+                // slot 1 is the second and last user of a slab: hand every slab back as soon as its MMAs are issued, so
+                // that the next layer's weights stream in underneath this layer's remaining MMAs (one commit per slab
+                // either way; with a single hand-back at the end of the layer the ~1500-cycle L2 round trip of the
+                // reload sat between MMA(l, slot 1) and MMA(l+1, slot 0))
+                if (slot == 1) umma_commit_pair(bar(kBarWEmpty + s), 3);
               }
               __syncwarp();
             }
@@ -543,53 +558,71 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       }
     }
     __syncwarp();
+  } else if (warp > kEpiWarps + 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));      // idle warps of the helper warpgroup
   } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     // ============ producer (both CTAs): own half of every weight slab + the modulation vectors of my tiles ============
-    // Order per iteration: mods(0), then for every layer l >= 1: mods(l), weights(l).  The modulations of a phase are
-    // always requested before the producer can block on a weight slab that (transitively) waits for that phase.
-    if (lane == 0) {
+    // Order per iteration: for every layer l >= 1: mods(l) [+ mods(0) of the next iteration after l = L-2], weights(l).
+    // The modulations of a phase are always requested before the producer can block on a weight slab that
+    // (transitively) waits for that phase.
+    // The whole warp runs the loops converged and one elected lane issues the copies (as in the MMA issuer): from
+    // `if (lane == 0)` every cp.async.bulk was wrapped in an ELECT / R2UR waterfall and the unrolled producer was
+    // 48 KB of straight-line code streaming through the SM's instruction caches once per iteration.
+    {
       uint32_t ev = 0;
       Walk w;
       w.set_block(S);
-      for (long long it = 0; it < S.total; ++it, w.next(S)) {
-        const bool full = w.type < S.n_full;
-        const int nsub = full ? 1 : S.ksub;
-        long long patch[2][kMaxSub];
-#pragma unroll
+      // modulation vectors of the two slots' tiles of the walk position ww, layer l, ring sequence number itx * L + l
+      auto issue_mods_of = [&](long long itx, int l, const Walk& ww) {
+        const uint32_t use = (uint32_t)itx * (uint32_t)L + (uint32_t)l;
+        const uint32_t stage = use & (kModStages - 1);
+        const bool full = ww.type < S.n_full;
+        const int ns = full ? 1 : S.ksub;
+#pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
-          const int ti = w.j * 4 + slot * 2 + (int)rank;
-#pragma unroll
-          for (int s = 0; s < kMaxSub; ++s) {
-            int pl = full ? ti : ti * S.ksub + s;
-            if (pl >= w.nps) pl = w.nps - 1;                     // phantom tile / missing patch: any valid vector
-            patch[slot][s] = P.idx ? (long long)P.idx[S.pa + w.base + pl] : S.pa + w.base + pl;
+          const uint32_t full_bar = bar(kBarModFull + slot * kModStages + stage);
+          mbar_wait_backoff(bar(kBarModEmpty + slot * kModStages + stage), ((use / kModStages) & 1u) ^ 1u, P.errflag, 10);
+          const int ti = ww.j * 4 + slot * 2 + (int)rank;
+#pragma unroll 1
+          for (int sidx = 0; sidx < ns; ++sidx) {
+            int pl = full ? ti : ti * S.ksub + sidx;
+            if (pl >= ww.nps) pl = ww.nps - 1;                   // phantom tile / missing patch: any valid vector
+            const long long patch = P.idx ? (long long)P.idx[S.pa + ww.base + pl] : S.pa + ww.base + pl;
+            if (elect_one()) {
+              if (sidx == 0) mbar_expect_tx(full_bar, (uint32_t)ns * kH * 4u);
+              bulk_g2s(sMods + (uint32_t)(((stage * 2 + slot) * kMaxSub + sidx) * kH * 4),
+                       P.mods + (size_t)l * layer_stride + (size_t)patch * kH, kH * 4, full_bar);
+            }
+            __syncwarp();
           }
         }
-        auto issue_mods = [&](int l) {
-          const uint32_t use = (uint32_t)it * (uint32_t)L + (uint32_t)l;
-          const uint32_t stage = use & (kModStages - 1);
-#pragma unroll
-          for (int slot = 0; slot < 2; ++slot) {
-            const uint32_t full_bar = bar(kBarModFull + slot * kModStages + stage);
-            mbar_wait_backoff(bar(kBarModEmpty + slot * kModStages + stage), ((use / kModStages) & 1u) ^ 1u, P.errflag, 10);
-            mbar_expect_tx(full_bar, (uint32_t)nsub * kH * 4u);
-            for (int s = 0; s < nsub; ++s)
-              bulk_g2s(sMods + (uint32_t)(((stage * 2 + slot) * kMaxSub + s) * kH * 4),
-                       P.mods + (size_t)l * layer_stride + (size_t)patch[slot][s] * kH, kH * 4, full_bar);
-          }
-        };
-        issue_mods(0);
+      };
+      // The layer-0 vectors of iteration it+1 are requested in the middle of iteration it (after layer L-2's request:
+      // their ring stage is the one an early layer of iteration it has released by then).
+      if (S.total > 0) issue_mods_of(0, 0, w);
+      const int l_early = L - 2 >= 1 ? L - 2 : 1;
+#pragma unroll 1
+      for (long long it = 0; it < S.total; ++it) {
+        Walk wn = w;
+        wn.next(S);
+#pragma unroll 1
         for (int l = 1; l < L; ++l, ++ev) {
-          issue_mods(l);
+          issue_mods_of(it, l, w);
+          if (l == l_early && it + 1 < S.total) issue_mods_of(it + 1, 0, wn);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(P.w16q) + ((size_t)(l - 1) * 2 + rank) * kLayerBytes;
 #pragma unroll 1
-          for (int s = 0; s < kNumSlabs; ++s) {
-            const uint32_t bytes = s < 4 ? kSlabBytes : kBiasSlabBytes;
-            mbar_wait_backoff(bar(kBarWEmpty + s), (ev & 1u) ^ 1u, P.errflag, 7);
-            mbar_expect_tx(bar(kBarWFull + s), bytes);
-            bulk_g2s(sW + s * kSlabBytes, src + (size_t)s * kSlabBytes, bytes, bar(kBarWFull + s));
+          for (int sl = 0; sl < kNumSlabs; ++sl) {
+            const uint32_t bytes = sl < 4 ? kSlabBytes : kBiasSlabBytes;
+            mbar_wait_backoff(bar(kBarWEmpty + sl), (ev & 1u) ^ 1u, P.errflag, 7);
+            if (elect_one()) {
+              mbar_expect_tx(bar(kBarWFull + sl), bytes);
+              bulk_g2s(sW + sl * kSlabBytes, src + (size_t)sl * kSlabBytes, bytes, bar(kBarWFull + sl));
+            }
+            __syncwarp();
           }
         }
+        w = wn;
       }
     }
     __syncwarp();

@@ -39,10 +39,10 @@ PATCHES_PER_SLICE, COORDS_PER_PATCH = 400, 576
 FLOP_PER_COORD = 4 * 2 * 256 * 256                       # tensor-eligible hidden contractions
 METRIC = "reconstructed 320x320 slices/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of the synthesis kernel from the ncu --set full capture in
-# profiles/r01_ncu_siren_v5.txt (136.77 MB + 40.91 MB for 64 slices, the v5 kernel with sub-block walking);
+# profiles/r01_ncu_siren_v5_final.txt (136.34 MB + 40.60 MB for 64 slices, the v5 kernel with sub-block walking);
 # algorithmic: 400 x 5 KB of modulations read + 400 x 2304 B of outputs written per slice = 2.97 MB (part of the
 # output is still in L2 when the kernel ends)
-DRAM_TRAFFIC_BYTES_PER_SLICE = (136.77e6 + 40.91e6) / 64
+DRAM_TRAFFIC_BYTES_PER_SLICE = (136.34e6 + 40.60e6) / 64
 MODEL_KW = dict(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=1.0, w0_initial=30.0,
                 use_bias=True, dropout=0.1, modulate=True, encoder_type="custom", encoder_path=None,
                 outer_patch_size=32, inner_patch_size=16, siren_patch_size=24)
@@ -83,17 +83,22 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
                 continue
+            try:
+                pw.append(float(r[2]))
+            except Exception:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "power_w": statistics.median(pw) if pw else None}
 
 
 def build_state_dict(activation: str, seed: int = 0):
@@ -343,7 +348,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None,
                          "traffic": DRAM_TRAFFIC_BYTES_PER_SLICE * kern_patches / PATCHES_PER_SLICE / max(len(events), 1),
-                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_ncu_siren_v5.txt",
+                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_ncu_siren_v5_final.txt (64 slices)",
                          "kernel": "siren_tc5_kernel (fused modulated-SIREN MLP, tcgen05 cta_group::2)", "peak_source": f"{peak_src}, sustained bf16",
                          "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
                          "kernel_ms_per_step": kern_ms / args.steps, "kernel_launches_timed": len(events),

@@ -188,6 +188,72 @@ patches_to_image_vec4_kernel(const float* __restrict__ tiles, const float* __res
                                                     __fdiv_rn(acc.z, norm.z), __fdiv_rn(acc.w, norm.w));
 }
 
+// The same gather for compile-time (I, K) with K <= 2 I (the reference's 16 / 24 and 16 / 32): at most 2 x 2 patches
+// cover a pixel, so all (up to eight) loads of a thread are issued before the first addition instead of one
+// dependent DRAM round trip per contribution, the window arithmetic has no run-time divisions, and the image index
+// comes from blockIdx.y.  Additions in the scalar kernel's order (py descending, then px descending): bit-identical.
+template <int I, int K>
+__global__ void __launch_bounds__(256)
+patches_to_image_fixed_kernel(const float* __restrict__ tiles, const float* __restrict__ weights,
+                              const uint8_t* __restrict__ black, long long N, int nV, int nH, float* __restrict__ out) {
+  static_assert(K <= 2 * I && I % 4 == 0 && K % 4 == 0 && ((K - I) / 2) % 4 == 0, "at most two patches per axis");
+  constexpr int padq = (K - I) / 2, KK = K * K;
+  const int OW4 = (nH * I) >> 2;
+  const int per_img = nV * I * OW4;
+  const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rem >= per_img) return;
+  const int y = rem / OW4, x = (rem - y * OW4) << 2;
+  const int yp = y + padq, xp = x + padq;
+  const int py_hi = min(yp / I, nV - 1);
+  const int py_lo = (yp - K + 1 <= 0) ? 0 : (yp - K + I) / I;
+  const int px_hi = min(xp / I, nH - 1);
+  const int px_lo = (xp + 3 - K + 1 <= 0) ? 0 : (xp + 3 - K + I) / I;
+  const bool two_y = py_lo < py_hi, two_x = px_lo < px_hi;
+  const int ky0 = yp - I * py_hi, ky1 = yp - I * py_lo, kx0 = xp - I * px_hi, kx1 = xp - I * px_lo;
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long n = blockIdx.y; n < N; n += gridDim.y) {
+    const long long pb = n * (long long)nV * nH;
+    const long long p00 = pb + py_hi * nH + px_hi, p01 = pb + py_hi * nH + px_lo;
+    const long long p10 = pb + py_lo * nH + px_hi, p11 = pb + py_lo * nH + px_lo;
+    // every load first ...
+    float4 w00 = one, w01 = one, w10 = one, w11 = one;
+    if (weights) {
+      w00 = __ldg(reinterpret_cast<const float4*>(weights + ky0 * K + kx0));
+      if (two_x) w01 = __ldg(reinterpret_cast<const float4*>(weights + ky0 * K + kx1));
+      if (two_y) w10 = __ldg(reinterpret_cast<const float4*>(weights + ky1 * K + kx0));
+      if (two_y && two_x) w11 = __ldg(reinterpret_cast<const float4*>(weights + ky1 * K + kx1));
+    }
+    bool b00 = false, b01 = false, b10 = false, b11 = false;
+    if (black) {
+      b00 = black[p00] != 0;
+      if (two_x) b01 = black[p01] != 0;
+      if (two_y) b10 = black[p10] != 0;
+      if (two_y && two_x) b11 = black[p11] != 0;
+    }
+    float4 t00 = zero, t01 = zero, t10 = zero, t11 = zero;
+    if (!b00) t00 = __ldg(reinterpret_cast<const float4*>(tiles + p00 * KK + ky0 * K + kx0));
+    if (two_x && !b01) t01 = __ldg(reinterpret_cast<const float4*>(tiles + p01 * KK + ky0 * K + kx1));
+    if (two_y && !b10) t10 = __ldg(reinterpret_cast<const float4*>(tiles + p10 * KK + ky1 * K + kx0));
+    if (two_y && two_x && !b11) t11 = __ldg(reinterpret_cast<const float4*>(tiles + p11 * KK + ky1 * K + kx1));
+    // ... then the additions in fold order
+    float4 acc = zero, norm = zero;
+    auto add = [&](const float4& t, const float4& w) {
+      acc.x = __fadd_rn(acc.x, __fmul_rn(t.x, w.x)); norm.x = __fadd_rn(norm.x, w.x);
+      acc.y = __fadd_rn(acc.y, __fmul_rn(t.y, w.y)); norm.y = __fadd_rn(norm.y, w.y);
+      acc.z = __fadd_rn(acc.z, __fmul_rn(t.z, w.z)); norm.z = __fadd_rn(norm.z, w.z);
+      acc.w = __fadd_rn(acc.w, __fmul_rn(t.w, w.w)); norm.w = __fadd_rn(norm.w, w.w);
+    };
+    add(t00, w00);
+    if (two_x) add(t01, w01);
+    if (two_y) {
+      add(t10, w10);
+      if (two_x) add(t11, w11);
+    }
+    reinterpret_cast<float4*>(out)[n * per_img + rem] = make_float4(__fdiv_rn(acc.x, norm.x), __fdiv_rn(acc.y, norm.y),
+                                                                   __fdiv_rn(acc.z, norm.z), __fdiv_rn(acc.w, norm.w));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // complex magnitude (fastmri.complex_abs at preprocessing.py:58): sqrt(re^2 + im^2), with the two
 // squares rounded separately as torch's (data**2).sum(-1).sqrt() does.
@@ -437,6 +503,18 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
   if (I % 4 == 0 && K % 4 == 0 && ((K - I) / 2) % 4 == 0 && aligned16(d_tiles) && aligned16(d_img) &&
       (d_weights == nullptr || aligned16(d_weights))) {
     const long long n_quads = n_pix / 4;
+    const long long per_img = n_quads / N;
+    if (I == 16 && (K == 24 || K == 32) && per_img < (1ll << 30)) {
+      dim3 grid((unsigned)((per_img + 255) / 256), (unsigned)(N < 65535 ? N : 65535));
+      if (K == 24)
+        patches_to_image_fixed_kernel<16, 24><<<grid, 256, 0, (cudaStream_t)stream>>>(d_tiles, d_weights, d_black, N, nV,
+                                                                                      nH, d_img);
+      else
+        patches_to_image_fixed_kernel<16, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(d_tiles, d_weights, d_black, N, nV,
+                                                                                      nH, d_img);
+      count_launch();
+      return check_launch("patches_to_image_fixed");
+    }
     patches_to_image_vec4_kernel<<<(unsigned)((n_quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_tiles, d_weights, d_black, n_quads, nV, nH, K, I, d_img);
     count_launch();

@@ -198,6 +198,13 @@ patches_to_image_fixed_kernel(const float* __restrict__ tiles, const float* __re
                               const uint8_t* __restrict__ black, long long N, int nV, int nH, float* __restrict__ out) {
   static_assert(K <= 2 * I && I % 4 == 0 && K % 4 == 0 && ((K - I) / 2) % 4 == 0, "at most two patches per axis");
   constexpr int padq = (K - I) / 2, KK = K * K;
+  // the K x K weight window is staged in shared memory once per CTA: four scattered 16-byte reads per thread and
+  // image otherwise go through the L1 tag stage next to the tile reads
+  __shared__ __align__(16) float s_w[KK];
+  if (weights) {
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) s_w[i] = weights[i];
+    __syncthreads();
+  }
   const int OW4 = (nH * I) >> 2;
   const int per_img = nV * I * OW4;
   const int rem = blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,6 +218,7 @@ patches_to_image_fixed_kernel(const float* __restrict__ tiles, const float* __re
   const bool two_y = py_lo < py_hi, two_x = px_lo < px_hi;
   const int ky0 = yp - I * py_hi, ky1 = yp - I * py_lo, kx0 = xp - I * px_hi, kx1 = xp - I * px_lo;
   const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
   for (long long n = blockIdx.y; n < N; n += gridDim.y) {
     const long long pb = n * (long long)nV * nH;
     const long long p00 = pb + py_hi * nH + px_hi, p01 = pb + py_hi * nH + px_lo;
@@ -218,10 +226,10 @@ patches_to_image_fixed_kernel(const float* __restrict__ tiles, const float* __re
     // every load first ...
     float4 w00 = one, w01 = one, w10 = one, w11 = one;
     if (weights) {
-      w00 = __ldg(reinterpret_cast<const float4*>(weights + ky0 * K + kx0));
-      if (two_x) w01 = __ldg(reinterpret_cast<const float4*>(weights + ky0 * K + kx1));
-      if (two_y) w10 = __ldg(reinterpret_cast<const float4*>(weights + ky1 * K + kx0));
-      if (two_y && two_x) w11 = __ldg(reinterpret_cast<const float4*>(weights + ky1 * K + kx1));
+      w00 = *reinterpret_cast<const float4*>(s_w + ky0 * K + kx0);
+      if (two_x) w01 = *reinterpret_cast<const float4*>(s_w + ky0 * K + kx1);
+      if (two_y) w10 = *reinterpret_cast<const float4*>(s_w + ky1 * K + kx0);
+      if (two_y && two_x) w11 = *reinterpret_cast<const float4*>(s_w + ky1 * K + kx1);
     }
     bool b00 = false, b01 = false, b10 = false, b11 = false;
     if (black) {
@@ -258,12 +266,25 @@ patches_to_image_fixed_kernel(const float* __restrict__ tiles, const float* __re
 // complex magnitude (fastmri.complex_abs at preprocessing.py:58): sqrt(re^2 + im^2), with the two
 // squares rounded separately as torch's (data**2).sum(-1).sqrt() does.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cabs1(float re, float im) {
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+}
 __global__ void __launch_bounds__(256)
 complex_abs_kernel(const float2* __restrict__ in, long long n, float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float2 v = __ldg(in + i);
-  out[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+  out[i] = cabs1(v.x, v.y);
+}
+// four complex values per thread and a grid-stride loop (two 16-byte loads, one 16-byte store, several in flight)
+__global__ void __launch_bounds__(256)
+complex_abs_vec4_kernel(const float4* __restrict__ in, long long n4, float4* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll 2
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
+    out[i] = make_float4(cabs1(a.x, a.y), cabs1(a.z, a.w), cabs1(b.x, b.y), cabs1(b.z, b.w));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,7 +526,10 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
     const long long n_quads = n_pix / 4;
     const long long per_img = n_quads / N;
     if (I == 16 && (K == 24 || K == 32) && per_img < (1ll << 30)) {
-      dim3 grid((unsigned)((per_img + 255) / 256), (unsigned)(N < 65535 ? N : 65535));
+      // a thread walks several images (same pixel position: the window arithmetic and the weights are reused)
+      long long gy = (N + 3) / 4;
+      if (gy > 65535) gy = 65535;
+      dim3 grid((unsigned)((per_img + 255) / 256), (unsigned)gy);
       if (K == 24)
         patches_to_image_fixed_kernel<16, 24><<<grid, 256, 0, (cudaStream_t)stream>>>(d_tiles, d_weights, d_black, N, nV,
                                                                                       nH, d_img);
@@ -529,8 +553,16 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
 extern "C" int mrinr_complex_abs(const float* d_in, int64_t n, float* d_out, void* stream) {
   if (n == 0) return 0;
   MRINR_REQUIRE(d_in && d_out && n >= 0, MRINR_E_ARG, "mrinr_complex_abs: bad arguments");
-  complex_abs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2*>(d_in), n, d_out);
+  if ((n & 3) == 0 && aligned16(d_in) && aligned16(d_out)) {
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    complex_abs_vec4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(d_in), n4,
+                                                                             reinterpret_cast<float4*>(d_out));
+  } else {
+    complex_abs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(d_in), n, d_out);
+  }
   count_launch();
   return check_launch("complex_abs");
 }

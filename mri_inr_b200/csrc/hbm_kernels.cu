@@ -56,16 +56,24 @@ image_to_patches_kernel(const float* __restrict__ img, long long n_patches, int 
   const int q_per_row = O / 4;
   const int total_q = O * q_per_row;
   const int y0 = I * py - pad, x0 = I * px - pad;
+  // x0 + s is a multiple of 4 when I and pad are; rows are 16-byte aligned when W is a multiple of 4
+  const bool vec_ok = ((I | pad | W) & 3) == 0 && aligned16(img);
   float sum = 0.f;
+#pragma unroll 4
   for (int q = lane; q < total_q; q += 32) {
     const int r = q / q_per_row;
     const int s = (q - r * q_per_row) * 4;
     const float* row = src + (long long)reflect_idx(y0 + r, H) * W;
     float4 v;
-    v.x = __ldg(row + reflect_idx(x0 + s + 0, W));
-    v.y = __ldg(row + reflect_idx(x0 + s + 1, W));
-    v.z = __ldg(row + reflect_idx(x0 + s + 2, W));
-    v.w = __ldg(row + reflect_idx(x0 + s + 3, W));
+    const int xs = x0 + s;
+    if (vec_ok && xs >= 0 && xs + 3 < W) {
+      v = __ldg(reinterpret_cast<const float4*>(row + xs));      // interior: one aligned 16-byte load
+    } else {
+      v.x = __ldg(row + reflect_idx(xs + 0, W));
+      v.y = __ldg(row + reflect_idx(xs + 1, W));
+      v.z = __ldg(row + reflect_idx(xs + 2, W));
+      v.w = __ldg(row + reflect_idx(xs + 3, W));
+    }
     dst[q] = v;
     sum += (v.x + v.y) + (v.z + v.w);
   }

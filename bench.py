@@ -188,7 +188,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from mri_inr_b200 import _lib
-    from mri_inr_b200.dist import gather_slices, shard_range
+    from mri_inr_b200.dist import PeerGather, gather_slices, shard_range
     from mri_inr_b200.pipeline import ReconstructionPipeline
     from mri_inr_b200.synthetic import synthetic_slices
 
@@ -219,8 +219,22 @@ def run_ours(args):
 
     # synthetic undersampled slices of this rank's block (set-up, untimed); seeds depend on the global index
     images = synthetic_slices(n_local, IMG, IMG, device=dev, seed=1234 + s0)
-    recon = torch.empty(n_local, IMG, IMG, dtype=torch.float32, device=dev)
-    gathered = torch.empty(n_total, IMG, IMG, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    # The one exchange step (reconstructed slices -> rank 0).  Default: rank 0's final [n_total,320,320] buffer is
+    # mapped into every process over NVLink peer access and each rank's reassembly kernel stores its slices straight
+    # into it (compute and exchange in one kernel, chunk by chunk).  --exchange nccl, or a box without peer access:
+    # local buffer + point-to-point NCCL gather at the end of the step.
+    peer, exchange = None, "single GPU"
+    if world > 1:
+        exchange = "NCCL gather (point-to-point) after the last chunk"
+        if args.exchange == "peer":
+            try:
+                peer = PeerGather(n_total, (IMG, IMG), dev, dst=0)
+                exchange = "fused into the reassembly kernel: stores into rank 0's buffer over NVLink peer memory (CUDA IPC)"
+            except RuntimeError as e:
+                print(f"[bench] rank {rank}: {e}; falling back to the NCCL gather", file=sys.stderr)
+    recon = peer.local_view if peer is not None else torch.empty(n_local, IMG, IMG, dtype=torch.float32, device=dev)
+    gathered = (torch.empty(n_total, IMG, IMG, dtype=torch.float32, device=dev)
+                if (world > 1 and rank == 0 and peer is None) else None)
     black_frac = float((images.reshape(n_local, -1).amax(dim=1) == 0).float().mean()) if n_local else 0.0
 
     def barrier():
@@ -231,7 +245,7 @@ def run_ours(args):
 
     def step(events=None):
         pipe.reconstruct(images, out=recon, kernel_events=events)
-        if world > 1:
+        if world > 1 and peer is None:
             gather_slices(recon, n_total, dst=0, out=gathered)
 
     for _ in range(args.warmup):
@@ -302,9 +316,14 @@ def run_ours(args):
             pipe.reconstruct_from_host(host_in, host_out=shared_out[s0:s1], device=dev)
         else:
             pipe.reconstruct_from_host(host_in, device_out=recon, device=dev)
-            gather_slices(recon, n_total, dst=0, out=gathered)
-            if rank == 0:
-                host_out.copy_(gathered, non_blocking=True)
+            if peer is not None:
+                full = peer.finish()
+                if rank == 0:
+                    host_out.copy_(full, non_blocking=True)
+            else:
+                gather_slices(recon, n_total, dst=0, out=gathered)
+                if rank == 0:
+                    host_out.copy_(gathered, non_blocking=True)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_step()
@@ -337,7 +356,7 @@ def run_ours(args):
             "config": {"workload": f"baseline modulated SIREN ({args.activation}) batched inference over a synthetic "
                                    f"940-volume-shaped set: {n_total} slices 320x320 (acc 6 / cf 0.05), random-init "
                                    f"weights; patches -> encoder -> modulator -> fused tcgen05 MLP -> weighted reassembly",
-                       "slices": n_total, "chunk_slices": args.chunk, "parallelism": f"slices block-partitioned x{world}",
+                       "slices": n_total, "chunk_slices": args.chunk, "parallelism": f"slices block-partitioned x{world}", "exchange": exchange,
                        "precision": f"{args.precision} operands, fp32 accumulate", "black_patch_fraction": black_frac,
                        "coords_per_s": value * PATCHES_PER_SLICE * COORDS_PER_PATCH,
                        "l2": f"inputs larger than L2 ({n_local * IMG * IMG * 4 / 1e6:.0f} MB of slices per rank per step; "
@@ -362,6 +381,9 @@ def run_ours(args):
             os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if peer is not None:
+            recon = None
+            peer.close()
         dist.barrier()
         if rank == 0:
             try:
@@ -384,6 +406,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--ref-slices", type=int, default=4, help="slices per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the reconstructed slices reach rank 0 (see run_ours)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

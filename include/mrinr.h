@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRINR_ABI_VERSION 2
+#define MRINR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MRINR_API __attribute__((visibility("default")))
@@ -186,6 +186,21 @@ MRINR_API int mrinr_kspace_to_image(const float* d_kspace, const uint8_t* d_colm
 MRINR_API int64_t mrinr_image_metrics_scratch_bytes(int64_t N);
 MRINR_API int mrinr_image_metrics(const float* d_original, const float* d_predicted, int64_t N, int32_t H, int32_t W,
                         double* d_out, void* d_scratch, int64_t scratch_bytes, void* stream);
+
+/* ---- peer memory for the one exchange step (gather of reconstructed slices to one rank) ---- */
+/* The reference has no distributed code; the multi-GPU sweep gathers every rank's reconstructed slices on one rank.
+ * Instead of a collective after the reassembly, the gathering rank exports its [n_total,H,W] buffer and every other
+ * process maps it (CUDA IPC over NVLink / NVSwitch peer access), so that mrinr_patches_to_image on rank r stores
+ * its slices straight into the final buffer: compute and exchange are one kernel.
+ *   mrinr_peer_alloc : cudaMalloc `bytes` on the current device and export it -> d_ptr, handle (MRINR_PEER_HANDLE_BYTES)
+ *   mrinr_peer_open  : map an exported buffer into this process, peer access from the current device enabled lazily
+ *   mrinr_peer_close : unmap (opener), mrinr_peer_free: release (owner)
+ * All four are host-synchronous set-up calls (not on the data path). */
+#define MRINR_PEER_HANDLE_BYTES 64
+MRINR_API int mrinr_peer_alloc(int64_t bytes, void** d_ptr, uint8_t* handle);
+MRINR_API int mrinr_peer_open(const uint8_t* handle, void** d_ptr);
+MRINR_API int mrinr_peer_close(void* d_ptr);
+MRINR_API int mrinr_peer_free(void* d_ptr);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MRINR_LIB") or os.path.join(_HERE, "lib", "libmrinr.so")
 
 # include/mrinr.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_SINE, ACT_MORLET = 0, 1
 PREC_FP16, PREC_BF16, PREC_FP32 = 0, 1, 2
 PRECISIONS = {"fp16": PREC_FP16, "bf16": PREC_BF16, "fp32": PREC_FP32}
@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "mrinr_complex_abs", "mrinr_minmax_normalize",
     "mrinr_image_metrics_scratch_bytes", "mrinr_image_metrics",
     "mrinr_fft2c_workspace_bytes", "mrinr_fft2c", "mrinr_kspace_to_image",
+    "mrinr_peer_alloc", "mrinr_peer_open", "mrinr_peer_close", "mrinr_peer_free",
 )
 
 
@@ -105,6 +106,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrinr_complex_abs.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.mrinr_minmax_normalize.restype = c_int
     lib.mrinr_minmax_normalize.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.mrinr_peer_alloc.restype = c_int
+    lib.mrinr_peer_alloc.argtypes = [c_int64, POINTER(c_void_p), c_void_p]
+    lib.mrinr_peer_open.restype = c_int
+    lib.mrinr_peer_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.mrinr_peer_close.restype = c_int
+    lib.mrinr_peer_close.argtypes = [c_void_p]
+    lib.mrinr_peer_free.restype = c_int
+    lib.mrinr_peer_free.argtypes = [c_void_p]
 
 
 def load() -> ctypes.CDLL:

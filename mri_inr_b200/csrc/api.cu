@@ -337,3 +337,44 @@ extern "C" int mrinr_encoder_forward(const MrinrPacked* p, const float* d_patche
   return launch_dense_split(c3, 64, 64, nullptr, 0, 0, p->d_enc_wfs, p->d_enc_bf, p->Z, /*none*/ 0, 0.f, d_latent, p->Z,
                             B, p->d_errflag, st);
 }
+
+// ---- peer memory (include/mrinr.h: the exchange step fused into the reassembly kernel) ----------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == MRINR_PEER_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int mrinr_peer_alloc(int64_t bytes, void** d_ptr, uint8_t* handle) {
+  MRINR_REQUIRE(bytes > 0 && d_ptr && handle, MRINR_E_ARG, "mrinr_peer_alloc: bad arguments");
+  void* p = nullptr;
+  MRINR_CUDA(cudaMalloc(&p, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  memcpy(handle, &h, sizeof(h));
+  *d_ptr = p;
+  return 0;
+}
+
+extern "C" int mrinr_peer_open(const uint8_t* handle, void** d_ptr) {
+  MRINR_REQUIRE(handle && d_ptr, MRINR_E_ARG, "mrinr_peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  MRINR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *d_ptr = p;
+  return 0;
+}
+
+extern "C" int mrinr_peer_close(void* d_ptr) {
+  if (!d_ptr) return 0;
+  MRINR_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+}
+
+extern "C" int mrinr_peer_free(void* d_ptr) {
+  if (!d_ptr) return 0;
+  MRINR_CUDA(cudaFree(d_ptr));
+  return 0;
+}

@@ -1,5 +1,6 @@
 // Shared host/device helpers for libmrinr (sm_100a only).
 #pragma once
+#include <atomic>
 
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -32,6 +33,26 @@ int  check_launch(const char* what);   // cudaPeekAtLastError -> code (+message)
       return (int)_e;                                                             \
     }                                                                             \
   } while (0)
+
+// "Do this once per device": the opt-in to more than 48 KB of dynamic shared memory (cudaFuncSetAttribute) is a
+// per-device property of a kernel, so a process-wide `static bool` is wrong as soon as one process drives two GPUs
+// (and racy between host threads).  One bit per device ordinal; setting the attribute twice is harmless.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask[4];          // 256 device ordinals
+  bool need(int dev) const { return !(mask[(dev >> 6) & 3].load(std::memory_order_acquire) & (1ull << (dev & 63))); }
+  void done(int dev) { mask[(dev >> 6) & 3].fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+#define MRINR_SMEM_OPT_IN(kernel_expr, bytes)                                                                     \
+  do {                                                                                                            \
+    static DeviceOnce once_;                                                                                      \
+    int dev_ = 0;                                                                                                 \
+    MRINR_CUDA(cudaGetDevice(&dev_));                                                                             \
+    if (once_.need(dev_)) {                                                                                       \
+      MRINR_CUDA(cudaFuncSetAttribute((kernel_expr), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      once_.done(dev_);                                                                                           \
+    }                                                                                                             \
+  } while (0)
+
 
 __host__ __device__ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -408,11 +408,7 @@ extern "C" int mrinr_modulator_forward(const MrinrPacked* p, const float* d_late
   }
   if (p->H == 256 && p->Z <= 256) {
     const size_t smem_t = (size_t)3 * 256 * MT_LD * sizeof(float);
-    static bool configured_t = false;
-    if (!configured_t) {
-      MRINR_CUDA(cudaFuncSetAttribute(modulator_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-      configured_t = true;
-    }
+    MRINR_SMEM_OPT_IN((modulator_tiled_kernel), (int)smem_t);
     const long long grid_t = (B + MT_P - 1) / MT_P;
     modulator_tiled_kernel<<<(unsigned)grid_t, 256, smem_t, (cudaStream_t)stream>>>(d_latent, B, p->Z, p->L, p->d_mod_wT,
                                                                                   p->d_mod_bias, d_mods);

@@ -264,11 +264,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
 
 template <int N>
 static int launch_n(const DenseParams& P, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    MRINR_CUDA(cudaFuncSetAttribute(dense_split_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<N>::kSmemBytes));
-    configured = true;
-  }
+  MRINR_SMEM_OPT_IN((dense_split_kernel<N>), Cfg<N>::kSmemBytes);
   long long grid = (P.M + kBM - 1) / kBM;
   grid = (grid + kCluster - 1) / kCluster * kCluster;      // whole clusters; the extra CTAs only help with the weights
   dense_split_kernel<N><<<(unsigned)grid, kThreads, Cfg<N>::kSmemBytes, st>>>(P);

@@ -165,11 +165,7 @@ encoder_conv_kernel(const float* __restrict__ patches, long long B, const float*
 int launch_encoder_conv(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,
                         const float* b2, float* d_out, int num_sms, cudaStream_t st) {
   const size_t smem = sizeof(enc::Smem);
-  static bool configured = false;
-  if (!configured) {
-    MRINR_CUDA(cudaFuncSetAttribute(enc::encoder_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  MRINR_SMEM_OPT_IN((enc::encoder_conv_kernel), (int)smem);
   if (B <= 0) return 0;
   long long grid = (long long)num_sms;
   const long long groups = (B + enc::kP - 1) / enc::kP;

@@ -312,12 +312,7 @@ encoder_conv_tc_kernel(const float* __restrict__ patches, long long B, const flo
 
 int launch_encoder_conv_tc(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,
                            const float* b2, float* d_out, int num_sms, int32_t* errflag, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    MRINR_CUDA(cudaFuncSetAttribute(enctc::encoder_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    enctc::kSmemBytes));
-    configured = true;
-  }
+  MRINR_SMEM_OPT_IN((enctc::encoder_conv_tc_kernel), enctc::kSmemBytes);
   if (B <= 0) return 0;
   long long grid = (long long)num_sms;
   const long long pairs = (B + 1) / 2;

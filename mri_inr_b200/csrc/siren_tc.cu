@@ -267,12 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) siren_tc_v1_kernel(const SirenTcP
 
 template <int ACT, bool BF16, bool W0ONE>
 static int launch_one_v1(const SirenTcParams& P, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    MRINR_CUDA(cudaFuncSetAttribute(siren_tc_v1_kernel<ACT, BF16, W0ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSmemBytes));
-    configured = true;
-  }
+  MRINR_SMEM_OPT_IN((siren_tc_v1_kernel<ACT, BF16, W0ONE>), kSmemBytes);
   siren_tc_v1_kernel<ACT, BF16, W0ONE><<<grid, kThreads, kSmemBytes, st>>>(P);
   count_launch();
   return check_launch("siren_tc");

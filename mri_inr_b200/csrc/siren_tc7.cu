@@ -572,12 +572,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 
 template <int ACT, bool BF16, bool W0ONE>
 static int launch_one(const SirenTcParams& P, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    MRINR_CUDA(cudaFuncSetAttribute(siren_tc7_kernel<ACT, BF16, W0ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSmemBytes));
-    configured = true;
-  }
+  MRINR_SMEM_OPT_IN((siren_tc7_kernel<ACT, BF16, W0ONE>), kSmemBytes);
   siren_tc7_kernel<ACT, BF16, W0ONE><<<grid, kThreads, kSmemBytes, st>>>(P);
   count_launch();
   return check_launch("siren_tc7");

@@ -4,6 +4,7 @@ distributed code; this follows north_star's sharding statement.  Works on NCCL (
 """
 from __future__ import annotations
 
+import ctypes
 from typing import List, Optional, Tuple
 
 import torch
@@ -57,3 +58,84 @@ def gather_slices(local: torch.Tensor, n_total: int, dst: int = 0, out: Optional
         for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, dst, group)]):
             req.wait()
     return None
+
+
+class _RawCudaBuffer:
+    """Minimal ``__cuda_array_interface__`` carrier: lets ``torch.as_tensor`` alias a raw device pointer."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerGather:
+    """The exchange step without a collective: rank ``dst`` owns the final ``[n_total, *item_shape]`` fp32 buffer,
+    exports it with CUDA IPC, and every other rank maps it over NVLink / NVSwitch peer access.  ``local_view`` is
+    this rank's block of the FINAL buffer (``shard_range``): pass it as ``out=`` to
+    ``ReconstructionPipeline.reconstruct`` and the reassembly kernel stores the slices where they belong -- compute
+    and exchange are one kernel, chunk by chunk.  ``finish()`` (stream sync + barrier) makes the buffer readable on
+    ``dst``.  Raises ``RuntimeError`` when peer mapping is unavailable (callers fall back to ``gather_slices``).
+
+    One node, one process per GPU, every GPU visible to every process (the torchrun default)."""
+
+    def __init__(self, n_total: int, item_shape, device: torch.device, dst: int = 0, group=None):
+        from . import _lib
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerGather needs an initialised process group")
+        self.lib = _lib.load()
+        self.group, self.dst = group, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        self.shape = (int(n_total),) + tuple(int(x) for x in item_shape)
+        nbytes = 4
+        for x in self.shape:
+            nbytes *= x
+        self._ptr = ctypes.c_void_p()
+        self._owner = self.rank == dst
+        handle = torch.zeros(64, dtype=torch.uint8)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            if self._owner:
+                buf = (ctypes.c_uint8 * 64)()
+                rc = self.lib.mrinr_peer_alloc(nbytes, ctypes.byref(self._ptr), buf)
+                if rc != 0:
+                    status += 1
+                handle = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+            hdev = handle.to(self.device)
+            dist.broadcast(hdev, src=dst, group=group)
+            if not self._owner:
+                raw = bytes(hdev.cpu().numpy().tobytes())
+                buf = (ctypes.c_uint8 * 64).from_buffer_copy(raw)
+                rc = self.lib.mrinr_peer_open(buf, ctypes.byref(self._ptr))
+                if rc != 0:
+                    status += 1
+            dist.all_reduce(status, group=group)
+            if int(status.item()) != 0:
+                self.close()
+                raise RuntimeError("PeerGather: CUDA IPC / peer access unavailable: "
+                                   + self.lib.mrinr_last_error().decode(errors="replace"))
+            self.full = torch.as_tensor(_RawCudaBuffer(self._ptr.value, self.shape, "<f4"), device=self.device)
+        s, e = shard_range(n_total, self.rank, self.world)
+        self.local_view = self.full[s:e]
+
+    def finish(self) -> Optional[torch.Tensor]:
+        """Every rank's stores are complete and visible on ``dst``.  Returns the full buffer on ``dst``."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        return self.full if self._owner else None
+
+    def close(self) -> None:
+        if getattr(self, "_ptr", None) is not None and self._ptr.value:
+            self.full = self.local_view = None
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                if self._owner:
+                    if dist.is_initialized():
+                        dist.barrier(group=self.group)        # nobody still maps it
+                    self.lib.mrinr_peer_free(self._ptr)
+                else:
+                    self.lib.mrinr_peer_close(self._ptr)
+                    if dist.is_initialized():
+                        dist.barrier(group=self.group)
+            self._ptr = ctypes.c_void_p()

@@ -606,3 +606,22 @@ def test_earlier_kernel_variants_still_agree(variant):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_peer_gather_two_gpus():
+    """dist.PeerGather (the exchange step fused into the reassembly kernel: stores into rank 0's buffer over NVLink
+    peer memory) is bit-identical to a single-GPU reconstruction and to the NCCL gather.  Needs two GPUs."""
+    import subprocess
+    import sys
+    import os
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", "tools/check_peer_gather.py"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

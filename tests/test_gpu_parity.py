@@ -625,3 +625,34 @@ def test_peer_gather_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29541", "tools/check_peer_gather.py"],
                        cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "PEER_GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_ffma_encoder_variant_still_agrees():
+    """MRINR_ENC_VARIANT=ffma selects the all-FFMA convolution kernel (encoder_conv.cu) that the tensor-core conv2
+    (encoder_conv_tc.cu) replaced; it is kept for A/B measurements and must stay correct.  The choice is latched per
+    process, so it runs in a subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, '.')\n"
+        "from oracle import siren as o\n"
+        "from oracle.synth import synth_tiles\n"
+        "from tests.test_gpu_parity import _model, MODEL_CASES\n"
+        "n, kw, act, mk = MODEL_CASES[1]\n"
+        "m, sd = _model(kw, act, mk, 'fp16')\n"
+        "t = synth_tiles(5, 131)\n"
+        "with torch.no_grad():\n"
+        "    z = m.encoder(torch.from_numpy(t).cuda()).cpu().numpy()\n"
+        "want = o.model_forward(sd, torch.from_numpy(t), activation=act, return_intermediates=True)[1].numpy()\n"
+        "err = float(np.abs(z - want).max())\n"
+        "print('ERR', err)\n"
+        "assert err <= 1e-5\n"
+    )
+    env = dict(os.environ, MRINR_ENC_VARIANT="ffma")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -522,6 +522,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t b_lo = b_lo0 + (uint32_t)s * (kSlabBytes >> 4);
+#ifndef MRINR_POWER_NO_MMA     // tools/power_split.py only: wrong results, the tensor core stays idle
                 if (s < 4) {
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk)
@@ -530,6 +531,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
                 } else {
                   umma_f16_pair_lohi(d_tmem, ones_lo, b_lo, desc_hi, idesc, 1u);      // + bias
                 }
+#endif
                 // slot 1 is the second and last user of a slab: hand every slab back as soon as its MMAs are issued, so
                 // that the next layer's weights stream in underneath this layer's remaining MMAs (one commit per slab
                 // either way; with a single hand-back at the end of the layer the ~1500-cycle L2 round trip of the

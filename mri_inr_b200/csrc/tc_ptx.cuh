@@ -292,7 +292,11 @@ __device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) {
 // interleave: sines of group g, then the multiplies and packs of group g-1.
 __device__ __forceinline__ float vsin(float x) {
   float y;
+#ifdef MRINR_POWER_NO_SIN      // tools/power_split.py only: wrong results, the special-function unit stays idle
+  asm volatile("mul.f32 %0, %1, 0f3F000000;" : "=f"(y) : "f"(x));
+#else
   asm volatile("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#endif
   return y;
 }
 __device__ __forceinline__ float vmul(float a, float b) {

@@ -83,9 +83,14 @@ __device__ __forceinline__ void small_dft(float2 (&v)[R], float sgn) {
 // transforms a warp owns one sequence and its lanes stride over the butterflies; for column transforms the
 // sequence index is the fastest (kG is a power of two).  k = j mod Ns uses a mask while Ns is a power of two
 // (radices 4 and 2 come first in the plan), a modulo only in the trailing radix-3/5 stages.
-template <int R, bool COLS>
-__device__ __forceinline__ void stage(const float2* __restrict__ x, float2* __restrict__ y, int n, int Ns, int ss, int es,
+// NC / NSC: compile-time n and Ns (0 = run time).  With both known every index computation folds to shifts, masks and
+// immediate offsets; the generic instantiation spends more than half of its instructions on them (ncu: ALU pipe
+// 39-51 %, FMA 27-33 %).  The arithmetic and its order are the same, so the results are bit-identical.
+template <int R, bool COLS, int NC = 0, int NSC = 0>
+__device__ __forceinline__ void stage(const float2* __restrict__ x, float2* __restrict__ y, int n_rt, int Ns_rt, int ss, int es,
                                       const float2* __restrict__ tw, float sgn) {
+  const int n = NC ? NC : n_rt;
+  const int Ns = NSC ? NSC : Ns_rt;
   const int nb = n / R;
   const int tstep = n / (Ns * R);
   const bool pow2 = (Ns & (Ns - 1)) == 0;
@@ -130,6 +135,28 @@ __device__ __forceinline__ const float2* run_stages(float2* a, float2* b, const 
   return x;
 }
 
+// The same plan as make_plan() (radices 4, then 2, then 3, then 5) unrolled at compile time for a fixed length.
+template <bool COLS, int NC, int NS, int REM>
+struct FixedStages {
+  static __device__ __forceinline__ const float2* run(float2* x, float2* y, int ss, int es, const float2* tw, float sgn) {
+    constexpr int R = (REM % 4 == 0) ? 4 : (REM % 2 == 0) ? 2 : (REM % 3 == 0) ? 3 : 5;
+    static_assert(REM % R == 0, "length must be a product of 2, 3 and 5");
+    stage<R, COLS, NC, NS>(x, y, NC, NS, ss, es, tw, sgn);
+    __syncthreads();
+    return FixedStages<COLS, NC, NS * R, REM / R>::run(y, x, ss, es, tw, sgn);
+  }
+};
+template <bool COLS, int NC, int NS>
+struct FixedStages<COLS, NC, NS, 1> {
+  static __device__ __forceinline__ const float2* run(float2* x, float2*, int, int, const float2*, float) { return x; }
+};
+template <bool COLS, int NC>
+__device__ __forceinline__ const float2* run_plan(float2* a, float2* b, const Plan& plan, int ss, int es, const float2* tw,
+                                                  float sgn) {
+  if (NC != 0) return FixedStages<COLS, NC ? NC : 1, 1, NC ? NC : 1>::run(a, b, ss, es, tw, sgn);
+  return run_stages<COLS>(a, b, plan, ss, es, tw, sgn);
+}
+
 __device__ __forceinline__ void build_twiddles(float2* tw, int n, float sgn) {
   for (int i = threadIdx.x; i < n; i += kThreads) {
     float s, c;
@@ -139,11 +166,12 @@ __device__ __forceinline__ void build_twiddles(float2* tw, int n, float sgn) {
 }
 
 // rows: in [n_rows, n] complex -> out [n_rows, n] complex; centred (shift by n/2 on both sides), orthonormal
+template <int NC>
 __global__ void __launch_bounds__(kThreads)
 rows_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmask, float2* __restrict__ out, long long n_rows,
             Plan plan, float sgn, float scale) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int n = plan.n;
+  const int n = NC ? NC : plan.n;
   const int ss = n + 1;
   float2* tw = reinterpret_cast<float2*>(smem_raw);
   float2* a = tw + n;
@@ -164,7 +192,7 @@ rows_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmask, 
     a[g * ss + m] = v;
   }
   __syncthreads();
-  const float2* r = run_stages<false>(a, b, plan, ss, 1, tw, sgn);
+  const float2* r = run_plan<false, NC>(a, b, plan, ss, 1, tw, sgn);
   if (row0 + g < n_rows) {
     for (int o = threadIdx.x & 31; o < n; o += 32) {   // o = index in the destination row (coalesced)
       // fftshift: out[o] = r[(o - n/2) mod n]
@@ -177,12 +205,12 @@ rows_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmask, 
 }
 
 // columns: in [N, H, W] complex, transform along H for kG adjacent columns; complex or magnitude output
-template <bool ABS>
+template <bool ABS, int NC>
 __global__ void __launch_bounds__(kThreads)
 cols_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __restrict__ out_abs, int H, int W, Plan plan,
             float sgn, float scale) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int n = plan.n;                           // == H
+  const int n = NC ? NC : plan.n;                 // == H
   float2* tw = reinterpret_cast<float2*>(smem_raw);
   float2* a = tw + n;
   float2* b = a + kG * n;
@@ -200,7 +228,7 @@ cols_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __
     a[m * kG + g] = v;
   }
   __syncthreads();
-  const float2* r = run_stages<true>(a, b, plan, 1, kG, tw, sgn);
+  const float2* r = run_plan<true, NC>(a, b, plan, 1, kG, tw, sgn);
   for (int w = threadIdx.x; w < kG * n; w += kThreads) {
     const int g = w & (kG - 1), o = w / kG;
     if (x0 + g >= W) continue;
@@ -240,19 +268,34 @@ static int run(const float* d_in, const uint8_t* d_colmask, long long N, int H, 
   const float sgn = inverse ? 1.f : -1.f;
   const size_t smem_r = (size_t)(W + 2 * kG * (W + 1)) * sizeof(float2);
   const size_t smem_c = (size_t)(H + 2 * kG * H) * sizeof(float2);
-  MRINR_CUDA(cudaFuncSetAttribute(rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-  MRINR_CUDA(cudaFuncSetAttribute(cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-  MRINR_CUDA(cudaFuncSetAttribute(cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
   const long long n_rows = N * H;
   float2* tmp = static_cast<float2*>(d_ws);
-  rows_kernel<<<(unsigned)((n_rows + kG - 1) / kG), kThreads, smem_r, st>>>(reinterpret_cast<const float2*>(d_in), d_colmask, tmp,
-                                                                         n_rows, pw, sgn, 1.0f / sqrtf((float)W));
-  dim3 grid((W + kG - 1) / kG, (unsigned)N);
-  if (d_out_abs)
-    cols_kernel<true><<<grid, kThreads, smem_c, st>>>(tmp, nullptr, d_out_abs, H, W, ph, sgn, 1.0f / sqrtf((float)H));
-  else
-    cols_kernel<false><<<grid, kThreads, smem_c, st>>>(tmp, reinterpret_cast<float2*>(d_out_c), nullptr, H, W, ph, sgn,
-                                                     1.0f / sqrtf((float)H));
+  const float2* in2 = reinterpret_cast<const float2*>(d_in);
+  const unsigned grid_r = (unsigned)((n_rows + kG - 1) / kG);
+  const dim3 grid_c((W + kG - 1) / kG, (unsigned)N);
+  const float sw = 1.0f / sqrtf((float)W), sh = 1.0f / sqrtf((float)H);
+  // (the shared-memory size depends on the length, so the opt-in is renewed on every call)
+  // lengths with a compile-time plan (the reference's knee slices are 320 x 320); everything else: run-time plan
+#define MRINR_FFT_ROWS(NC)                                                                                  \
+  do {                                                                                                      \
+    MRINR_CUDA(cudaFuncSetAttribute(rows_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)); \
+    rows_kernel<NC><<<grid_r, kThreads, smem_r, st>>>(in2, d_colmask, tmp, n_rows, pw, sgn, sw);            \
+  } while (0)
+#define MRINR_FFT_COLS(NC)                                                                                  \
+  do {                                                                                                      \
+    if (d_out_abs) {                                                                                        \
+      MRINR_CUDA(cudaFuncSetAttribute(cols_kernel<true, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c)); \
+      cols_kernel<true, NC><<<grid_c, kThreads, smem_c, st>>>(tmp, nullptr, d_out_abs, H, W, ph, sgn, sh);  \
+    } else {                                                                                                \
+      MRINR_CUDA(cudaFuncSetAttribute(cols_kernel<false, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c)); \
+      cols_kernel<false, NC><<<grid_c, kThreads, smem_c, st>>>(tmp, reinterpret_cast<float2*>(d_out_c), nullptr, H, W, ph, \
+                                                               sgn, sh);                                    \
+    }                                                                                                       \
+  } while (0)
+  if (W == 320) MRINR_FFT_ROWS(320); else if (W == 256) MRINR_FFT_ROWS(256); else MRINR_FFT_ROWS(0);
+  if (H == 320) MRINR_FFT_COLS(320); else if (H == 256) MRINR_FFT_COLS(256); else MRINR_FFT_COLS(0);
+#undef MRINR_FFT_ROWS
+#undef MRINR_FFT_COLS
   count_launch(2);
   return check_launch("fft2c");
 }

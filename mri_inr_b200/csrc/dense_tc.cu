@@ -12,6 +12,9 @@
 //   A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi        (the dropped lo.lo term is 2^-22 relative),
 // accumulated in fp32 in TMEM: ~1e-6 relative, i.e. the noise level of an fp32 FFMA loop with a different summation
 // order.  tests/test_gpu_parity.py holds the result to 1e-5 against the reference.
+// Operand range: hi and lo are fp16, so the split is exact to 2^-22 only for 6.1e-5 <= |x| < 65504 (below that the
+// absolute floor is the fp16 subnormal spacing 6e-8, above it hi overflows).  The reference's inputs are images
+// normalised to [0, 1] (normalize_scan, preprocessing.py:127-137) and its weights / activations are O(1).
 //
 // Per CTA: one 128-row tile, all N columns (N = 64, 128 or 256), K in slabs of 32 through a 2-stage ring (96 KB for
 // N = 256), so that TWO CTAs are resident per SM: one CTA's prologue / epilogue (all latency) hides behind the

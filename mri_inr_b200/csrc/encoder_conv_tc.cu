@@ -23,7 +23,8 @@
 // The zero padding of the convolution is the two border lines, written once.
 //
 // Precision: as in dense_tc.cu -- every fp32 operand is split into hi = rn16(x), lo = rn16(x - hi) and a product is
-// three MMAs (lo.hi + hi.lo + hi.hi, fp32 accumulation in TMEM): ~1e-6 relative, tests hold 1e-5.
+// three MMAs (lo.hi + hi.lo + hi.hi, fp32 accumulation in TMEM): ~1e-6 relative, tests hold 1e-5 (operand range as
+// stated in dense_tc.cu: conv1 outputs of [0, 1]-normalised patches are O(1)).
 //
 // Roles per CTA (persistent, one per SM): kGroups warpgroups of 4 warps, each running its own pipeline over pairs
 //   stage 2 patches -> conv1 (FFMA2, 2 warps per patch) -> [epilogue of the group's previous pair: tcgen05.ld, bias,

@@ -279,10 +279,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         float s[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          const float mg[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float x = __uint_as_float(v[g * 4 + i]);
-            s[g * 4 + i] = vsin(W0ONE ? x : P.w0 * x);
+            s[g * 4 + i] = vsin_live(W0ONE ? x : P.w0 * x, mg[i]);
           }
           if (g > 0) {
             const float4 mm = m[g - 1];
@@ -338,8 +339,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           const float x2 = __uint_as_float(v[g * 4 + 2]), x3 = __uint_as_float(v[g * 4 + 3]);
           float h0, h1, h2, h3;
           if (ACT == MRINR_ACT_SINE) {
-            h0 = vsin(W0ONE ? x0 : P.w0 * x0); h1 = vsin(W0ONE ? x1 : P.w0 * x1);
-            h2 = vsin(W0ONE ? x2 : P.w0 * x2); h3 = vsin(W0ONE ? x3 : P.w0 * x3);
+            h0 = vsin_live(W0ONE ? x0 : P.w0 * x0, mw[g].x); h1 = vsin_live(W0ONE ? x1 : P.w0 * x1, mw[g].y);
+            h2 = vsin_live(W0ONE ? x2 : P.w0 * x2, mw[g].z); h3 = vsin_live(W0ONE ? x3 : P.w0 * x3, mw[g].w);
           } else {
             h0 = act_fast<ACT, W0ONE>(x0, P.w0); h1 = act_fast<ACT, W0ONE>(x1, P.w0);
             h2 = act_fast<ACT, W0ONE>(x2, P.w0); h3 = act_fast<ACT, W0ONE>(x3, P.w0);

@@ -299,6 +299,20 @@ __device__ __forceinline__ float vsin(float x) {
 #endif
   return y;
 }
+// Sine of a feature whose modulation is m: with MRINR_V5_SKIP_DEAD (measurement builds only, `make skipdead`) the
+// special-function instruction is predicated off when m == 0 -- the product sin(x) * 0 is 0 either way.
+__device__ __forceinline__ float vsin_live(float x, float m) {
+#ifdef MRINR_V5_SKIP_DEAD
+  // a warp vote makes the branch uniform (ptxas speculates a lane-predicated sin.approx: MUFU.SIN + select); a tile's
+  // rows share their patch's modulation, so the vote is unanimous except in the two-patch remainder tiles
+  float y = 0.f;
+  if (__any_sync(0xffffffffu, m != 0.f)) y = vsin(x);
+  return y;
+#else
+  (void)m;
+  return vsin(x);
+#endif
+}
 __device__ __forceinline__ float vmul(float a, float b) {
   float y;
   asm volatile("mul.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));

@@ -10,6 +10,17 @@ from tools.diag_gpu import build, DEV
 from mri_inr_b200 import ops
 
 
+ZERO_FRAC = float(os.environ.get("MRINR_ZERO_FRAC", "0"))
+
+
+def _mods(L, Bp):
+    """Modulations in [0, 0.5); MRINR_ZERO_FRAC of them exactly 0 (ReLU outputs: about half at random init)."""
+    m = torch.rand(L, Bp, 256, device=DEV) * 0.5
+    if ZERO_FRAC > 0:
+        m = m * (torch.rand(L, Bp, 256, device=DEV) >= ZERO_FRAC)
+    return m
+
+
 def main():
     nslices = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -23,7 +34,7 @@ def main():
             p16, p32 = m16._packed(), m32._packed()
             for Bp in (1, 3, 130, 401, 2500):
                 torch.manual_seed(Bp)
-                mods = torch.rand(L, Bp, 256, device=DEV) * 0.5
+                mods = _mods(L, Bp)
                 y16 = torch.full((Bp, 576), 7.0, device=DEV)
                 y32 = torch.empty(Bp, 576, device=DEV)
                 ops.siren_forward(p16, mods, out=y16)
@@ -38,7 +49,7 @@ def main():
         Bp = 400 * nslices
         packed = m._packed()
         torch.manual_seed(0)
-        mods = torch.rand(L, Bp, 256, device=DEV) * 0.5
+        mods = _mods(L, Bp)
         out = torch.empty(Bp, 576, device=DEV)
         ops.siren_forward(packed, mods, out=out)
         torch.cuda.synchronize()

@@ -2,7 +2,12 @@
 """Headline benchmark (BASELINE.json): reconstructed 320x320 slices/s of the modulated-SIREN inference path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--activation sine|morlet]
+                    [--num-layers L --latent-dim Z] [--mods random-init|dense] [--precision fp16|fp16x3|bf16|fp32|auto]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+
+BASELINE.json configs: [1] default flags; [2] --activation morlet; [3] --num-layers 9 --latent-dim 128 (the
+"residual-connection ablation shape": deeper MLP, reduced latent; SURVEY D4 -- the residual code itself is not in
+the reference snapshot); [4] --gpus 2|4|8 under torchrun.
 
 Workload (config[1] of BASELINE.json): baseline modulated SIREN, random-init weights (reference init ranges),
 batched inference over a synthetic 940-volume-shaped validation set = 940 volumes x 11 slices = 10 340 slices of
@@ -36,7 +41,7 @@ if ROOT not in sys.path:
 N_VOLUMES, SLICES_PER_VOLUME, IMG = 940, 11, 320
 N_SLICES = N_VOLUMES * SLICES_PER_VOLUME                 # 10 340
 PATCHES_PER_SLICE, COORDS_PER_PATCH = 400, 576
-FLOP_PER_COORD = 4 * 2 * 256 * 256                       # tensor-eligible hidden contractions
+FLOP_PER_LAYER_COORD = 2 * 256 * 256                     # one tensor-eligible hidden contraction
 METRIC = "reconstructed 320x320 slices/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of the synthesis kernel from the ncu --set full capture in
 # profiles/r01_ncu_siren_v5_final.txt (136.34 MB + 40.60 MB for 64 slices, the v5 kernel with sub-block walking);
@@ -101,19 +106,29 @@ class ClockSampler:
                 "power_w": statistics.median(pw) if pw else None}
 
 
-def build_state_dict(activation: str, seed: int = 0):
+def build_state_dict(activation: str, seed: int = 0, num_layers: int = 5, latent_dim: int = 256,
+                     mods: str = "random-init"):
     """Random-init weights of the baseline architecture with the reference's init ranges
-    (Siren.init_, modulated_siren.py:126-142; nn.Linear / nn.Conv2d defaults)."""
+    (Siren.init_, modulated_siren.py:126-142; nn.Linear / nn.Conv2d defaults).
+
+    ``mods="dense"``: trained-like modulations -- every modulator bias is shifted by +0.5, so the ReLU outputs are
+    dense and O(0.5) instead of ~50 % exact zeros of magnitude ~0.02; zero operands cost the
+    tensor core less energy, so the random-init figure flatters a power-limited kernel slightly."""
     import torch
 
     from mri_inr_b200.modulated_siren import ModulatedSiren
 
     torch.manual_seed(seed)
-    model = ModulatedSiren(device=torch.device("cpu"), activation=activation, **MODEL_KW)
+    kw = dict(MODEL_KW, num_layers=num_layers, latent_dim=latent_dim)
+    model = ModulatedSiren(device=torch.device("cpu"), activation=activation, **kw)
+    if mods == "dense":
+        with torch.no_grad():
+            for seq in model.modulator.layers:
+                seq[0].bias.add_(0.5)
     return model, {k: v.detach().clone() for k, v in model.state_dict().items()}
 
 
-def cpu_reference_rate(sd, slices_cpu, activation, n_warm=1, budget_s=20.0, max_slices=24):
+def cpu_reference_rate(sd, slices_cpu, activation, n_warm=1, budget_s=20.0, max_slices=24, num_layers=5):
     """slices/s of the reference's CPU op sequence (oracle/flow.py) on a bounded sample, all host threads."""
     import torch
 
@@ -121,10 +136,10 @@ def cpu_reference_rate(sd, slices_cpu, activation, n_warm=1, budget_s=20.0, max_
 
     torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core
     for i in range(n_warm):
-        flow.reconstruct_slice(sd, slices_cpu[i % len(slices_cpu)], activation=activation)
+        flow.reconstruct_slice(sd, slices_cpu[i % len(slices_cpu)], activation=activation, num_layers=num_layers)
     t0, n = time.perf_counter(), 0
     while n < max_slices and (n < 2 or time.perf_counter() - t0 < budget_s):
-        flow.reconstruct_slice(sd, slices_cpu[n % len(slices_cpu)], activation=activation)
+        flow.reconstruct_slice(sd, slices_cpu[n % len(slices_cpu)], activation=activation, num_layers=num_layers)
         n += 1
     dt = time.perf_counter() - t0
     return n / dt, n, torch.get_num_threads()
@@ -141,7 +156,8 @@ def run_reference(args):
     from mri_inr_b200.synthetic import column_mask  # noqa: F401  (host-only helper; no GPU needed here)
     import numpy as np
 
-    _, sd = build_state_dict(args.activation)
+    L = args.num_layers
+    _, sd = build_state_dict(args.activation, num_layers=L, latent_dim=args.latent_dim, mods=args.mods)
     # the same kind of input as the GPU arm, generated on the host (no GPU work in this arm)
     rs = np.random.RandomState(1234)
     sample = max(1, args.ref_slices)
@@ -159,11 +175,11 @@ def run_reference(args):
     from oracle import flow
 
     for _ in range(args.warmup):
-        flow.reconstruct_slice(sd, slices[0], activation=args.activation)
+        flow.reconstruct_slice(sd, slices[0], activation=args.activation, num_layers=L)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for s in slices:
-            flow.reconstruct_slice(sd, s, activation=args.activation)
+            flow.reconstruct_slice(sd, s, activation=args.activation, num_layers=L)
     dt = time.perf_counter() - t0
     rate = args.steps * sample / dt
     threads = torch.get_num_threads()
@@ -171,8 +187,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "slices/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"baseline modulated SIREN ({args.activation}) inference, {N_SLICES} synthetic 320x320 "
-                               f"slices (940 volumes x 11); CPU arm times a bounded sample of {sample} slice(s) per step",
+        "config": {"workload": f"{'baseline' if (L == 5 and args.latent_dim == 256) else f'num_layers={L}, latent_dim={args.latent_dim}'} "
+                               f"modulated SIREN ({args.activation}) inference, {N_SLICES} synthetic 320x320 "
+                               f"slices (940 volumes x 11), {args.mods} weights; CPU arm times a bounded sample of {sample} slice(s) per step",
+                   "num_layers": L, "latent_dim": args.latent_dim, "activation": args.activation, "modulations": args.mods,
                    "coords_per_s": rate * PATCHES_PER_SLICE * COORDS_PER_PATCH},
         "cpu_baseline": {"value": rate, "unit": "slices/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} slice(s)/step x {args.steps} steps, torch {torch.__version__} CPU, "
@@ -181,6 +199,71 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class SharedHostBuffer:
+    """ONE result buffer in POSIX shared memory that every rank maps and page-locks, so each rank streams its block
+    host -> device -> host over its own PCIe link (funnelling 4.2 GB through rank 0's link would serialise the
+    downloads).  Construction and ``close()`` are collective; if any rank fails, every rank ends up with ``ok == False``
+    (the callers then fall back to gather + one download on rank 0) and the collective sequence stays aligned."""
+
+    def __init__(self, n_total, img, rank, world, dev, s0, s1):
+        import torch
+        import torch.distributed as dist
+
+        self.rank, self.tensor, self._registered = rank, None, False
+        self.path = f"/dev/shm/mrinr_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}.bin"
+        nbytes = n_total * img * img * 4
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            try:
+                with open(self.path, "wb") as f:
+                    f.truncate(nbytes)
+            except Exception as e:                  # noqa: BLE001
+                flag += 1
+                print(f"[bench] rank {rank}: cannot create {self.path}: {e}", file=sys.stderr, flush=True)
+        dist.all_reduce(flag)                       # also the barrier behind which the file exists
+        if int(flag.item()) == 0:
+            try:
+                t = torch.from_file(self.path, shared=True, size=n_total * img * img, dtype=torch.float32)
+                rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister returned {rc}")
+                self._registered = True
+                self.tensor = t.view(n_total, img, img)
+                self.tensor[s0:s1].zero_()          # touch my pages
+            except Exception as e:                  # noqa: BLE001 - any failure selects the fallback on every rank
+                flag += 1
+                print(f"[bench] rank {rank}: shared host buffer unavailable ({e})", file=sys.stderr, flush=True)
+        dist.all_reduce(flag)
+        self.ok = int(flag.item()) == 0
+        if not self.ok:
+            self.close()
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+
+        if self.tensor is not None and self._registered:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        self.tensor = None
+        dist.barrier()                              # nobody maps the file any more
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def auto_chunk(n_local: int, target: int = 235) -> int:
+    """Chunk size near ``target`` that splits this rank's block evenly (no ragged last chunk: at N = 8 the block is
+    1 293 slices = 5 x 235 + 118, and the half-empty last launch cost 0.8 % of scaling efficiency in round 1)."""
+    if n_local <= 0:
+        return target
+    n_chunks = max(1, -(-n_local // target))
+    return -(-n_local // n_chunks)
 
 
 def run_ours(args):
@@ -211,11 +294,15 @@ def run_ours(args):
     n_total = args.slices
     s0, s1 = shard_range(n_total, rank, world)
     n_local = s1 - s0
+    L = args.num_layers
+    flop_per_coord = (L - 1) * FLOP_PER_LAYER_COORD
+    # every rank uses the chunk size of the largest block, so the per-launch work is the same on every rank
+    chunk = args.chunk if args.chunk > 0 else auto_chunk(shard_range(n_total, 0, world)[1])
 
-    model, sd = build_state_dict(args.activation)
+    model, sd = build_state_dict(args.activation, num_layers=L, latent_dim=args.latent_dim, mods=args.mods)
     model.to(dev).eval()
     model.precision = args.precision
-    pipe = ReconstructionPipeline(model, chunk_slices=args.chunk)
+    pipe = ReconstructionPipeline(model, chunk_slices=chunk)
 
     # synthetic undersampled slices of this rank's block (set-up, untimed); seeds depend on the global index
     images = synthetic_slices(n_local, IMG, IMG, device=dev, seed=1234 + s0)
@@ -228,14 +315,13 @@ def run_ours(args):
         exchange = "NCCL gather (point-to-point) after the last chunk"
         if args.exchange == "peer":
             try:
-                peer = PeerGather(n_total, (IMG, IMG), dev, dst=0)
+                peer = PeerGather(n_total, (IMG, IMG), dev, dst=0)      # collective; raises on every rank or on none
                 exchange = "fused into the reassembly kernel: stores into rank 0's buffer over NVLink peer memory (CUDA IPC)"
             except RuntimeError as e:
-                print(f"[bench] rank {rank}: {e}; falling back to the NCCL gather", file=sys.stderr)
+                print(f"[bench] rank {rank}: {e}; falling back to the NCCL gather", file=sys.stderr, flush=True)
     recon = peer.local_view if peer is not None else torch.empty(n_local, IMG, IMG, dtype=torch.float32, device=dev)
     gathered = (torch.empty(n_total, IMG, IMG, dtype=torch.float32, device=dev)
                 if (world > 1 and rank == 0 and peer is None) else None)
-    black_frac = float((images.reshape(n_local, -1).amax(dim=1) == 0).float().mean()) if n_local else 0.0
 
     def barrier():
         torch.cuda.synchronize()
@@ -251,6 +337,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    model.precision_selected = getattr(model._packed(), "precision", args.precision)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -266,54 +353,40 @@ def run_ours(args):
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    kern_ms = sum(a.elapsed_time(b) for a, b, _ in events)
-    kern_patches = sum(n for _, _, n in events)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    kern_ms = sum(a.elapsed_time(b) for a, b, _, _ in events)
+    kern_patches_handed = sum(n for _, _, n, _ in events)
+    # patches the synthesis kernel actually computed: its own device-side count of non-black patches per launch
+    kern_patches = int(sum(int(na.item()) if na is not None else n for _, _, n, na in events))
+    t = torch.tensor([ms_total, float(kern_patches_handed), float(kern_patches)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms_total = float(tmax[0].item())
+    black_frac = 1.0 - float(t[2].item()) / max(float(t[1].item()), 1.0)      # over all ranks
     value = args.steps * n_total / (ms_total * 1e-3)
 
     # ---- end to end: pinned host -> device -> pipeline -> pinned host, every step
-    # (every rank uploads its block; the reconstructed set lands in host memory of rank 0)
+    # (every rank uploads its block; the reconstructed set lands in host memory)
     host_in = torch.empty(n_local, IMG, IMG, dtype=torch.float32).pin_memory()
     host_in.copy_(images)
-    # Result buffer in host memory.  N = 1: a pinned tensor.  N > 1: ONE buffer in POSIX shared memory that every rank
-    # maps and page-locks, so each rank streams its block host -> device -> host over its own PCIe link (the NCCL
-    # gather belongs to the device-resident metric above; funnelling 4.2 GB through rank 0's link would serialise
-    # the downloads).  If shared memory is too small on the box, fall back to gather + one download on rank 0.
-    shared_out, e2e_mode = None, "pinned"
+    shared, e2e_mode = None, "pinned"
     if world > 1:
-        path = f"/dev/shm/mrinr_bench_{os.environ.get('MASTER_PORT', '0')}.bin"
-        ok = torch.zeros(1, dtype=torch.int32, device=dev)
-        try:
-            if rank == 0:
-                with open(path, "wb") as f:
-                    f.truncate(n_total * IMG * IMG * 4)
-            dist.barrier()
-            shared_out = torch.from_file(path, shared=True, size=n_total * IMG * IMG, dtype=torch.float32).view(n_total, IMG, IMG)
-            rc = torch.cuda.cudart().cudaHostRegister(shared_out.data_ptr(), shared_out.numel() * 4, 0)
-            if int(rc) != 0:
-                raise RuntimeError(f"cudaHostRegister failed: {rc}")
-            shared_out[s0:s1].zero_()               # touch my pages
-            ok += 1
-        except Exception as e:                      # noqa: BLE001 - any failure selects the fallback on every rank
-            print(f"[bench] rank {rank}: shared host buffer unavailable ({e}); e2e falls back to gather + download", file=sys.stderr)
-        dist.all_reduce(ok)
-        if int(ok.item()) == world:
+        shared = SharedHostBuffer(n_total, IMG, rank, world, dev, s0, s1)
+        if shared.ok:
             e2e_mode = "shared host buffer, one PCIe link per rank"
         else:
-            shared_out, e2e_mode = None, "NCCL gather to rank 0, then one download"
+            shared, e2e_mode = None, "gather to rank 0 on the device, then one download"
     host_out = None
-    if shared_out is None:
+    if shared is None:
         host_out = torch.empty(n_total if rank == 0 else 1, IMG, IMG, dtype=torch.float32).pin_memory()
 
     def e2e_step():
         # public API for host-resident slices: chunked, double-buffered upload / compute / download
         if world == 1:
             pipe.reconstruct_from_host(host_in, host_out=host_out, device=dev)
-        elif shared_out is not None:
-            pipe.reconstruct_from_host(host_in, host_out=shared_out[s0:s1], device=dev)
+        elif shared is not None:
+            pipe.reconstruct_from_host(host_in, host_out=shared.tensor[s0:s1], device=dev)
         else:
             pipe.reconstruct_from_host(host_in, device_out=recon, device=dev)
             if peer is not None:
@@ -333,10 +406,10 @@ def run_ours(args):
         e2e_step()
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_steps * n_total / (float(t.item()) * 1e-3)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * n_total / (float(t2.item()) * 1e-3)
 
     # one launch of the synthesis kernel after an idle pause: the kernel's rate before the power limiter reacts
     # (tools/burst_check.py); reported next to the sustained figure, never as the headline
@@ -356,41 +429,55 @@ def run_ours(args):
             ops.siren_forward(packed, bm, out=bo)
             b1.record()
             torch.cuda.synchronize()
-            burst = nb * COORDS_PER_PATCH * FLOP_PER_COORD / (b0.elapsed_time(b1) * 1e-3) / 1e12
+            burst = nb * COORDS_PER_PATCH * flop_per_coord / (b0.elapsed_time(b1) * 1e-3) / 1e12
             del bm, bo
         except Exception as e:  # noqa: BLE001 - an extra, never fatal
-            print(f"[bench] burst measurement skipped: {e}", file=sys.stderr)
+            print(f"[bench] burst measurement skipped: {e}", file=sys.stderr, flush=True)
     if rank == 0:
         peaks, peak_src = measured_peaks()
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-        achieved = (kern_patches * COORDS_PER_PATCH * FLOP_PER_COORD) / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+        achieved = (kern_patches * COORDS_PER_PATCH * flop_per_coord) / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+        prec = getattr(model, "precision_selected", args.precision)
+        mma_per_product = {"fp16x3": 3}.get(prec, 1)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, n, threads = cpu_reference_rate(sd, [images[i].cpu() for i in range(min(4, n_local))], args.activation)
+            rate, n, threads = cpu_reference_rate(sd, [images[i].cpu() for i in range(min(4, n_local))], args.activation,
+                                                  num_layers=L)
             cpu = {"value": rate, "unit": "slices/s", "cores": threads, "kind": "port",
                    "sample": f"{n} slices of the same workload through oracle/flow.py (reference op sequence), "
                              f"{threads} torch threads of {os.cpu_count()} cpus"}
+        shape = "baseline" if (L == 5 and args.latent_dim == 256) else f"num_layers={L}, latent_dim={args.latent_dim}"
         line = {
             "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else args.precision,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": {"fp16": "f16", "fp16x3": "f16x3 (split operands, fp32-class)"}.get(prec, prec),
             "data": "synthetic",
-            "config": {"workload": f"baseline modulated SIREN ({args.activation}) batched inference over a synthetic "
-                                   f"940-volume-shaped set: {n_total} slices 320x320 (acc 6 / cf 0.05), random-init "
-                                   f"weights; patches -> encoder -> modulator -> fused tcgen05 MLP -> weighted reassembly",
-                       "slices": n_total, "chunk_slices": args.chunk, "parallelism": f"slices block-partitioned x{world}", "exchange": exchange,
-                       "precision": f"{args.precision} operands, fp32 accumulate", "black_patch_fraction": black_frac,
-                       "coords_per_s": value * PATCHES_PER_SLICE * COORDS_PER_PATCH,
+            "config": {"workload": f"{shape} modulated SIREN ({args.activation}) batched inference over a synthetic "
+                                   f"940-volume-shaped set: {n_total} slices 320x320 (acc 6 / cf 0.05), "
+                                   f"{args.mods} weights; patches -> encoder -> modulator -> fused tcgen05 MLP -> "
+                                   f"weighted reassembly",
+                       "slices": n_total, "chunk_slices": chunk, "num_layers": L, "latent_dim": args.latent_dim,
+                       "activation": args.activation, "modulations": args.mods,
+                       "parallelism": f"slices block-partitioned x{world}", "exchange": exchange,
+                       "precision": f"{prec} operands, fp32 accumulate" + (f" (requested: {args.precision})" if prec != args.precision else ""),
+                       "black_patch_fraction": black_frac,
+                       "black_patch_note": "1 - (patches the synthesis kernel computed, its device-side count) / (patches handed to it)",
+                       "coords_per_s": value * PATCHES_PER_SLICE * COORDS_PER_PATCH * (1.0 - black_frac),
                        "l2": f"inputs larger than L2 ({n_local * IMG * IMG * 4 / 1e6:.0f} MB of slices per rank per step; "
-                             f"intermediates {args.chunk * 400 * (1024 + 5 * 256 + 576) * 4 / 1e6:.0f} MB per chunk)"},
+                             f"intermediates {chunk * 400 * (1024 + L * 256 + 576) * 4 / 1e6:.0f} MB per chunk)"},
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": n_total * IMG * IMG * 4,
                     "d2h_bytes_per_step": n_total * IMG * IMG * 4, "steps": e2e_steps, "result": e2e_mode},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None,
-                         "traffic": DRAM_TRAFFIC_BYTES_PER_SLICE * kern_patches / PATCHES_PER_SLICE / max(len(events), 1),
+                         "traffic": DRAM_TRAFFIC_BYTES_PER_SLICE * kern_patches / PATCHES_PER_SLICE / max(len(events), 1)
+                         if (L == 5) else None,
                          "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_ncu_siren_v5_final.txt (64 slices)",
                          "kernel": "siren_tc5_kernel (fused modulated-SIREN MLP, tcgen05 cta_group::2)", "peak_source": f"{peak_src}, sustained bf16",
+                         "flop_per_coord": flop_per_coord, "patches_billed": kern_patches,
+                         "patches_handed": kern_patches_handed,
+                         "tensor_flops_issued_per_algorithmic_flop": mma_per_product,
                          "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
                          "kernel_ms_per_step": kern_ms / args.steps, "kernel_launches_timed": len(events),
                          "kernel_share_of_step": kern_ms / ms_total,
@@ -404,17 +491,19 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+    # ---- teardown.  The measurement is complete and printed; every step below is collective and runs on every rank
+    # in the same order.  A failure here is reported on stderr but does not turn a finished measurement into rc != 0.
     if world > 1:
-        if peer is not None:
+        try:
             recon = None
-            peer.close()
-        dist.barrier()
-        if rank == 0:
-            try:
-                os.unlink(f"/dev/shm/mrinr_bench_{os.environ.get('MASTER_PORT', '0')}.bin")
-            except OSError:
-                pass
-        dist.destroy_process_group()
+            if shared is not None:
+                shared.close()
+            if peer is not None:
+                peer.close()
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: teardown: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
 
 
 def main():
@@ -424,9 +513,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--activation", default="sine", choices=["sine", "morlet"])
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--num-layers", type=int, default=5, help="hidden layers of the synthesis MLP (BASELINE config 3: 9)")
+    ap.add_argument("--latent-dim", type=int, default=256, choices=[64, 128, 256], help="BASELINE config 3: 128")
+    ap.add_argument("--mods", default="random-init", choices=["random-init", "dense"],
+                    help="dense: trained-like modulations (modulator biases + 0.5), see build_state_dict")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3", "bf16", "fp32", "auto"])
     ap.add_argument("--slices", type=int, default=N_SLICES)
-    ap.add_argument("--chunk", type=int, default=235)
+    ap.add_argument("--chunk", type=int, default=0, help="slices per launch; 0 = near 235, dividing the per-rank block evenly")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--ref-slices", type=int, default=4, help="slices per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -434,11 +527,26 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the reconstructed slices reach rank 0 (see run_ours)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    rank = os.environ.get("RANK", "0")
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    except BaseException as e:  # noqa: BLE001 - leave one line per failing rank in the tail of stderr, then re-raise
+        if not isinstance(e, SystemExit):
+            import traceback
+
+            tb = traceback.format_exc()
+            print(f"[bench] rank {rank}: FAILED: {type(e).__name__}: {e}\n{tb}", file=sys.stderr, flush=True)
+        raise
 
 
 if __name__ == "__main__":
+    try:
+        from torch.distributed.elastic.multiprocessing.errors import record
+
+        main = record(main)          # torchrun then prints the failing rank's traceback in its summary
+    except Exception:  # noqa: BLE001
+        pass
     main()

@@ -53,10 +53,10 @@ extern "C" {
  * Layout = src/networks/modulated_siren.py: SirenNet (:160-213), Modulator (:304-323), grid (:427-433). */
 typedef struct MrinrWeightsView {
   int32_t dim_in;            /* must be 2                                                      */
-  int32_t dim_hidden;        /* H; tensor-core path requires 256, fp32 path H % 32 == 0, <=256 */
+  int32_t dim_hidden;        /* H; tensor-core path requires 256, fp32 path H % 32 == 0, <=512 */
   int32_t dim_out;           /* must be 1 (modulated_siren.py:451-455 squeezes it)             */
   int32_t num_layers;        /* L hidden layers, 2..16                                         */
-  int32_t latent_dim;        /* Z, multiple of 4, <= 512                                       */
+  int32_t latent_dim;        /* Z, multiple of 4, <= 1024 (patch encoder: 64, 128 or 256)      */
   int32_t siren_patch_size;  /* S; coordinates per patch C = S*S                               */
   float   w0;                /* hidden layers 1..L-1 and the output layer                      */
   float   w0_initial;        /* layer 0                                                        */

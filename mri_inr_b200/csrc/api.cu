@@ -44,10 +44,10 @@ extern "C" int64_t mrinr_launch_count(void) { return (int64_t)g_launches.load();
 extern "C" void mrinr_free_packed(MrinrPacked* p) {
   if (!p) return;
   cudaFree(p->d_table0);
-  cudaFree(p->d_table16);
+  cudaFree(p->d_table16);    // lab builds only (null otherwise)
   cudaFree(p->d_net_wT);
-  cudaFree(p->d_net_w16);
-  cudaFree(p->d_net_w16p);
+  cudaFree(p->d_net_w16);    // lab
+  cudaFree(p->d_net_w16p);   // lab
   cudaFree(p->d_net_w16q);
   cudaFree(p->d_layer0);
   cudaFree(p->d_grid);
@@ -138,10 +138,12 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
   {
     const size_t mod_w_elems = (size_t)Z * H + (size_t)(L - 1) * (H + Z) * H;
     PK_CUDA(cudaMalloc(&p->d_table0, (size_t)C * H * sizeof(float)));
-    PK_CUDA(cudaMalloc(&p->d_table16, (size_t)C * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_wT, (size_t)(L - 1) * H * H * sizeof(float)));
+#ifdef MRINR_LAB   // operand copies of the retired kernel variants (lab/): not part of the product library
+    PK_CUDA(cudaMalloc(&p->d_table16, (size_t)C * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_w16, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_w16p, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
+#endif
     PK_CUDA(cudaMalloc(&p->d_net_w16q, (size_t)(L - 1) * 2 * (H / 8 + 2) * (H / 2) * 8 * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_layer0, (size_t)3 * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_grid, (size_t)C * 2 * sizeof(float)));
@@ -165,7 +167,9 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     if (b0) PK_CUDA(cudaMemcpyAsync(p->d_layer0 + 2 * H, b0, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PK_CUDA(cudaMemcpyAsync(p->d_grid, v->d_grid, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PK_RC(run_layer0_table(v->d_grid, v->d_net_weight[0], b0, C, H, p->w0_initial, p->activation, p->d_table0, st));
+#ifdef MRINR_LAB
     PK_RC(run_table16(p->d_table0, (long long)C * H, precision == MRINR_PREC_BF16, p->d_table16, st));
+#endif
     for (int l = 0; l < L; ++l) {
       if (v->d_net_bias && v->d_net_bias[l])
         PK_CUDA(cudaMemcpyAsync(p->d_net_bias + (size_t)l * H, v->d_net_bias[l], H * sizeof(float),
@@ -176,10 +180,12 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     for (int l = 1; l < L; ++l) {
       PK_RC(run_transpose(v->d_net_weight[l], H, H, p->d_net_wT + (size_t)(l - 1) * H * H, st));
       if (precision != MRINR_PREC_FP32) {
+#ifdef MRINR_LAB
         PK_RC(run_pack_w16(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
                            p->d_net_w16 + (size_t)(l - 1) * H * H, st));
         PK_RC(run_pack_w16_pair(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
                                 p->d_net_w16p + (size_t)(l - 1) * H * H, st));
+#endif
         PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], (v->d_net_bias ? v->d_net_bias[l] : nullptr), H,
                                      precision == MRINR_PREC_BF16,
                                      p->d_net_w16q + (size_t)(l - 1) * 2 * (H / 8 + 2) * (H / 2) * 8, st));
@@ -318,17 +324,20 @@ extern "C" int mrinr_encoder_forward(const MrinrPacked* p, const float* d_patche
   cudaStream_t st = (cudaStream_t)stream;
   float* c2 = static_cast<float*>(d_workspace);
   float* c3 = c2 + (size_t)B * 2048;
-  // conv1 + conv2: tensor-core implicit GEMM for conv2 (encoder_conv_tc.cu) unless MRINR_ENC_VARIANT=ffma selects the
-  // all-FFMA kernel (encoder_conv.cu), kept for A/B measurements
+  // conv1 + conv2: tensor-core implicit GEMM for conv2 (encoder_conv_tc.cu)
+  int rc;
+#ifdef MRINR_LAB   // lab library only: MRINR_ENC_VARIANT=ffma selects the retired all-FFMA kernel (lab/encoder_conv.cu)
   static int enc_variant = -1;
   if (enc_variant < 0) {
     const char* e = getenv("MRINR_ENC_VARIANT");
     enc_variant = (e && e[0] == 'f') ? 0 : 1;
   }
-  int rc = enc_variant
-               ? launch_encoder_conv_tc(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms,
-                                        p->d_errflag, st)
-               : launch_encoder_conv(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms, st);
+  if (!enc_variant)
+    rc = launch_encoder_conv(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms, st);
+  else
+#endif
+  rc = launch_encoder_conv_tc(d_patches, B, p->d_enc_c1w, p->d_enc_c1b, p->d_enc_c2w, p->d_enc_c2b, c2, p->num_sms,
+                              p->d_errflag, st);
   if (rc != 0) return rc;
   // Conv2d(32,64,8) on the 8x8 map == [B,2048] x [2048,64] (weight [64,32,8,8] flattens in the same (c,y,x) order)
   rc = launch_dense_split(c2, 2048, 2048, nullptr, 0, 0, p->d_enc_w3s, p->d_enc_b3, 64, /*leaky*/ 2, 0.2f, c3, 64, B,

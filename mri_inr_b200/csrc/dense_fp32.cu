@@ -368,11 +368,8 @@ int run_layer0_table(const float* grid, const float* w, const float* b, int C, i
 int launch_siren_fp32(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx,
                       const int32_t* d_nactive, int64_t B, float* d_out, cudaStream_t st) {
   const size_t smem = (size_t)2 * TM * p->H * sizeof(float) + 2 * TM * sizeof(int);
-  static int configured_for = -1;
-  if (configured_for != (int)smem) {
-    MRINR_CUDA(cudaFuncSetAttribute(siren_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_for = (int)smem;
-  }
+  // once per device, sized for the largest supported configuration (H = 512)
+  MRINR_SMEM_OPT_IN(siren_fp32_kernel, (size_t)2 * TM * 512 * sizeof(float) + 2 * TM * sizeof(int));
   const long long n_tiles = (B * p->C + TM - 1) / TM;
   long long grid = (long long)p->num_sms * 2;
   if (grid > n_tiles) grid = n_tiles;
@@ -416,11 +413,9 @@ extern "C" int mrinr_modulator_forward(const MrinrPacked* p, const float* d_late
     return check_launch("modulator_tiled");
   }
   const size_t smem = ((size_t)TM * p->Z + (size_t)2 * TM * p->H) * sizeof(float);
-  static int configured_for = -1;
-  if (configured_for != (int)smem) {
-    MRINR_CUDA(cudaFuncSetAttribute(modulator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_for = (int)smem;
-  }
+  MRINR_REQUIRE(smem <= 227 * 1024, MRINR_E_UNSUPPORTED, "modulator: H=%d Z=%d needs %zu bytes of shared memory", p->H,
+                p->Z, smem);
+  MRINR_SMEM_OPT_IN(modulator_kernel, 227 * 1024);
   const long long grid = (B + TM - 1) / TM;
   modulator_kernel<<<(unsigned)grid, p->H, smem, (cudaStream_t)stream>>>(d_latent, B, p->Z, p->H, p->L, p->d_mod_wT,
                                                                         p->d_mod_bias, d_mods);

@@ -680,6 +680,15 @@ int launch_siren_tc_v5(const MrinrPacked* p, const float* d_mods, const int32_t*
 }
 
 }  // namespace v5
+
+#ifndef MRINR_LAB
+// The product library ships exactly one tensor-core synthesis kernel (the lab library, `make lab`, routes this call
+// through lab/siren_dispatch.cu to the retired variants instead).
+int launch_siren_tc(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
+                    int64_t B, float* d_out, cudaStream_t st) {
+  return v5::launch_siren_tc_v5(p, d_mods, d_idx, d_nactive, B, d_out, st);
+}
+#endif
 }  // namespace mrinr
 
 #ifdef MRINR_TIMELINE

@@ -68,22 +68,57 @@ class _RawCudaBuffer:
                                          "data": (int(ptr), False), "version": 3, "strides": None}
 
 
+class _LibPeerBackend:
+    """CUDA IPC through the C ABI (``mrinr_peer_*``, include/mrinr.h).  Every method returns ``(rc, value)``; a
+    non-zero ``rc`` leaves the message in ``mrinr_last_error()``."""
+
+    def __init__(self):
+        from . import _lib
+
+        self.lib = _lib.load()
+
+    def alloc(self, nbytes: int):
+        ptr, buf = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+        rc = self.lib.mrinr_peer_alloc(nbytes, ctypes.byref(ptr), buf)
+        return rc, (ptr.value or 0, bytes(buf))
+
+    def open(self, handle: bytes):
+        ptr = ctypes.c_void_p()
+        rc = self.lib.mrinr_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(handle), ctypes.byref(ptr))
+        return rc, ptr.value or 0
+
+    def close(self, ptr: int) -> int:
+        return self.lib.mrinr_peer_close(ctypes.c_void_p(ptr))
+
+    def free(self, ptr: int) -> int:
+        return self.lib.mrinr_peer_free(ctypes.c_void_p(ptr))
+
+    def last_error(self) -> str:
+        return self.lib.mrinr_last_error().decode(errors="replace")
+
+    def as_tensor(self, ptr: int, shape, device) -> torch.Tensor:
+        return torch.as_tensor(_RawCudaBuffer(ptr, shape, "<f4"), device=device)
+
+
 class PeerGather:
     """The exchange step without a collective: rank ``dst`` owns the final ``[n_total, *item_shape]`` fp32 buffer,
     exports it with CUDA IPC, and every other rank maps it over NVLink / NVSwitch peer access.  ``local_view`` is
     this rank's block of the FINAL buffer (``shard_range``): pass it as ``out=`` to
     ``ReconstructionPipeline.reconstruct`` and the reassembly kernel stores the slices where they belong -- compute
     and exchange are one kernel, chunk by chunk.  ``finish()`` (stream sync + barrier) makes the buffer readable on
-    ``dst``.  Raises ``RuntimeError`` when peer mapping is unavailable (callers fall back to ``gather_slices``).
+    ``dst``.  Raises ``RuntimeError`` ON EVERY RANK when peer mapping is unavailable on any rank (callers fall back
+    to ``gather_slices``).
+
+    Collective discipline: construction, ``finish()`` and ``close()`` are collective calls, and every rank issues
+    exactly the same sequence of collectives whatever its local state is (a rank whose mapping failed still takes
+    part in the release barrier; otherwise the ranks' collective streams would be off by one from then on).
 
     One node, one process per GPU, every GPU visible to every process (the torchrun default)."""
 
-    def __init__(self, n_total: int, item_shape, device: torch.device, dst: int = 0, group=None):
-        from . import _lib
-
+    def __init__(self, n_total: int, item_shape, device: torch.device, dst: int = 0, group=None, backend=None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerGather needs an initialised process group")
-        self.lib = _lib.load()
+        self.backend = backend if backend is not None else _LibPeerBackend()
         self.group, self.dst = group, dst
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.device = torch.device(device)
@@ -91,51 +126,79 @@ class PeerGather:
         nbytes = 4
         for x in self.shape:
             nbytes *= x
-        self._ptr = ctypes.c_void_p()
+        self._ptr = 0
         self._owner = self.rank == dst
+        self.full = self.local_view = None
         handle = torch.zeros(64, dtype=torch.uint8)
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
+        err = ""
+        with self._device_ctx():
             if self._owner:
-                buf = (ctypes.c_uint8 * 64)()
-                rc = self.lib.mrinr_peer_alloc(nbytes, ctypes.byref(self._ptr), buf)
+                rc, (ptr, raw) = self.backend.alloc(nbytes)
                 if rc != 0:
                     status += 1
-                handle = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+                    err = self.backend.last_error()
+                else:
+                    self._ptr = ptr
+                    handle = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
             hdev = handle.to(self.device)
             dist.broadcast(hdev, src=dst, group=group)
-            if not self._owner:
-                raw = bytes(hdev.cpu().numpy().tobytes())
-                buf = (ctypes.c_uint8 * 64).from_buffer_copy(raw)
-                rc = self.lib.mrinr_peer_open(buf, ctypes.byref(self._ptr))
+            dist.all_reduce(status, group=group)             # did the owner get its buffer?
+            if int(status.item()) == 0 and not self._owner:
+                rc, ptr = self.backend.open(bytes(hdev.cpu().numpy().tobytes()))
                 if rc != 0:
                     status += 1
-            dist.all_reduce(status, group=group)
+                    err = self.backend.last_error()
+                else:
+                    self._ptr = ptr
+            dist.all_reduce(status, group=group)             # did every rank map it?
             if int(status.item()) != 0:
-                self.close()
-                raise RuntimeError("PeerGather: CUDA IPC / peer access unavailable: "
-                                   + self.lib.mrinr_last_error().decode(errors="replace"))
-            self.full = torch.as_tensor(_RawCudaBuffer(self._ptr.value, self.shape, "<f4"), device=self.device)
+                self._release()
+                raise RuntimeError(f"PeerGather: CUDA IPC / peer access unavailable on {int(status.item())} rank(s)"
+                                   + (f": {err}" if err else ""))
+            self.full = self.backend.as_tensor(self._ptr, self.shape, self.device)
         s, e = shard_range(n_total, self.rank, self.world)
         self.local_view = self.full[s:e]
 
+    def _device_ctx(self):
+        import contextlib
+
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+
+    def _sync(self) -> None:
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
     def finish(self) -> Optional[torch.Tensor]:
         """Every rank's stores are complete and visible on ``dst``.  Returns the full buffer on ``dst``."""
-        torch.cuda.synchronize(self.device)
+        self._sync()
         dist.barrier(group=self.group)
         return self.full if self._owner else None
 
+    def _release(self) -> None:
+        """(1) non-owners unmap, (2) ONE barrier that every rank takes whatever its local state, (3) the owner
+        frees -- so nobody still maps the buffer when it is freed, and the collective sequence is the same on every
+        rank even after a partial failure."""
+        errors = []
+        self.full = self.local_view = None
+        with self._device_ctx():
+            self._sync()
+            if self._ptr and not self._owner:
+                if self.backend.close(self._ptr) != 0:
+                    errors.append("mrinr_peer_close: " + self.backend.last_error())
+                self._ptr = 0
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            if self._ptr and self._owner:
+                if self.backend.free(self._ptr) != 0:
+                    errors.append("mrinr_peer_free: " + self.backend.last_error())
+                self._ptr = 0
+        if errors:
+            raise RuntimeError("PeerGather release failed: " + "; ".join(errors))
+
     def close(self) -> None:
-        if getattr(self, "_ptr", None) is not None and self._ptr.value:
-            self.full = self.local_view = None
-            with torch.cuda.device(self.device):
-                torch.cuda.synchronize(self.device)
-                if self._owner:
-                    if dist.is_initialized():
-                        dist.barrier(group=self.group)        # nobody still maps it
-                    self.lib.mrinr_peer_free(self._ptr)
-                else:
-                    self.lib.mrinr_peer_close(self._ptr)
-                    if dist.is_initialized():
-                        dist.barrier(group=self.group)
-            self._ptr = ctypes.c_void_p()
+        """Collective: call it on every rank (idempotent only across ALL ranks together)."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        self._release()

@@ -12,8 +12,7 @@ and runs on the hand-written sm_100a kernels of ``libmrinr.so``:
 * synthesis net over the coordinate grid of every patch: one persistent tcgen05 kernel
   (``mrinr_siren_forward``); the coordinates are the module's ``grid`` buffer, as in the reference (:448).
 
-``MRINR_ENCODER=cudnn`` routes the patch encoder through its PyTorch/cuDNN submodule instead (A/B aid).
-There is no CPU path: CPU tensors raise.
+There is no CPU path and no library (cuDNN / cuBLAS) route: CPU tensors and unsupported shapes raise.
 """
 from __future__ import annotations
 
@@ -152,16 +151,14 @@ class Encoder(nn.Module):
         return [seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[4].weight, seq[4].bias,
                 seq[7].weight, seq[7].bias]
 
-    def forward_torch(self, x):
-        """The same layers through PyTorch (cuDNN on a GPU): an A/B and debugging aid, not the product path."""
-        # fp32 like the reference's eval path (no TF32: the CPU reference is plain fp32)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            return self.fc(self.encoder(x))
-
     def forward(self, x, workspace=None):
         owner = self._owner() if self._owner is not None else None
-        if owner is None or os.environ.get("MRINR_ENCODER", "") == "cudnn" or tuple(x.shape[1:]) != (32, 32):
-            return self.forward_torch(x)
+        if owner is None:
+            raise RuntimeError("Encoder must belong to a ModulatedSiren")
+        if x.dim() != 3 or tuple(x.shape[1:]) != (32, 32):
+            # FixedAutoencoder is hard-wired to 32x32 inputs (siren_encoder.py:498-512: two stride-2 convolutions, then
+            # an 8x8 kernel on the 8x8 map); other sizes fail in the reference as well (Linear(64, .) shape mismatch)
+            raise RuntimeError(f"the custom encoder takes [B,32,32] patches, got {tuple(x.shape)}")
         return ops.encoder_forward(owner._packed(), x.to(torch.float32).contiguous(), workspace=workspace)
 
 
@@ -184,6 +181,9 @@ class ModulatedSiren(nn.Module):
         self.activation = activation
         self.dropout = float(dropout)
         self.precision = os.environ.get("MRINR_PRECISION", "fp16")
+        if outer_patch_size != 32 or latent_dim not in (64, 128, 256):
+            raise ValueError("mri_inr_b200: the custom patch encoder (siren_encoder.py:498-512) is built for "
+                             f"outer_patch_size=32 and latent_dim in (64, 128, 256); got {outer_patch_size}, {latent_dim}")
 
         self.net = SirenNet(dim_in, dim_hidden, dim_out, num_layers, w0, w0_initial, use_bias, dropout, activation)
         self.modulator = Modulator(latent_dim, dim_hidden, num_layers)
@@ -226,14 +226,10 @@ class ModulatedSiren(nn.Module):
                 mod_biases=[s[0].bias for s in self.modulator.layers],
                 w0=self.net.w0, w0_initial=self.net.w0_initial, activation=self.activation,
                 precision=self.precision, siren_patch_size=self.siren_patch_size,
-                encoder_params=self.encoder.params() if self._encoder_kernel_ok() else None,
+                encoder_params=self.encoder.params(),
                 outer_patch_size=self.outer_patch_size)
             self._pack_key = key
         return self._pack
-
-    def _encoder_kernel_ok(self) -> bool:
-        # the reference's custom encoder is hard-wired to 32x32 patches and a 64 -> latent_dim linear layer
-        return self.outer_patch_size == 32 and self.latent_dim in (64, 128, 256)
 
     def _check_inference(self) -> None:
         if self.training and self.dropout > 0:

@@ -73,7 +73,10 @@ class ReconstructionPipeline:
         tiles = ops.siren_forward(packed, mods, black=black, out=bufs["tiles"][:B], workspace=bufs["ws"])
         if kernel_events is not None:
             e1.record()
-            kernel_events.append((e0, e1, B))
+            # the kernel's own count of non-black patches (first word of its workspace, written by the compaction
+            # launch): what the kernel actually computed, as opposed to the B patches it was handed
+            nact = bufs["ws"][:4].view(torch.int32).clone() if black is not None else None
+            kernel_events.append((e0, e1, B, nact))
         ops.patches_to_image(tiles.view(B, S, S), n, (nV, nH), I, weights=bufs["wts"], black=black, out=out)
 
     @torch.no_grad()
@@ -81,8 +84,10 @@ class ReconstructionPipeline:
                     skip_black: bool = True, kernel_events: Optional[list] = None) -> torch.Tensor:
         """``images [N,H,W]`` (undersampled, fp32, CUDA) -> reconstructed ``[N, nV*I, nH*I]``.
 
-        ``kernel_events``: if a list is given, a ``(start, end, n_patches)`` CUDA-event pair bracketing every
-        synthesis-kernel launch is appended (recorded on the launching stream; used by bench.py's roofline)."""
+        ``kernel_events``: if a list is given, ``(start, end, n_patches, n_active)`` is appended for every
+        synthesis-kernel launch: a CUDA-event pair recorded on the launching stream around it, the patches handed to
+        it and a 1-element int32 device tensor with the non-black patches it computed (``None`` without black
+        skipping).  Used by bench.py's roofline."""
         m = self.model
         m._check_inference()
         if images.dim() != 3 or not images.is_cuda:

@@ -1,0 +1,50 @@
+"""Multi-GPU regression tests of bench.py's sweep (SCALE_r01: the N=4 point exited rc=1 on the driver's box).
+They need 2 / 4 GPUs on the box and skip otherwise; the CPU-side collective discipline is covered by
+tests/test_dist_gloo.py (gloo, world_size 2)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun_bench(n, port, extra):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), "bench.py", "--gpus", str(n)] + extra
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def _ngpus():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rep", [0, 1, 2])
+def test_bench_four_gpus_back_to_back(rep):
+    """The 4-GPU point of the sweep, three times back to back on fresh process groups (different ports)."""
+    if _ngpus() < 4:
+        pytest.skip("needs four GPUs")
+    line = _torchrun_bench(4, 29650 + rep, ["--steps", "2", "--warmup", "3", "--slices", "2068", "--no-burst"])
+    assert line["n_gpus"] == 4 and line["value"] > 0 and line["e2e"]["value"] > 0
+    assert "peer memory" in line["config"]["exchange"]
+
+
+@pytest.mark.gpu
+def test_bench_two_gpus_odd_chunk_count_and_ragged_blocks():
+    """Blocks of unequal size (1001 slices over 2 ranks = 501 + 500) in 3 chunks per rank (167 slices, the last one
+    ragged on rank 1): the double-buffered host path reuses its two staging buffers with an odd chunk count."""
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    line = _torchrun_bench(2, 29660, ["--steps", "2", "--warmup", "3", "--slices", "1001", "--chunk", "167", "--no-burst"])
+    assert line["n_gpus"] == 2 and line["config"]["chunk_slices"] == 167
+    line = _torchrun_bench(2, 29661, ["--steps", "2", "--warmup", "3", "--slices", "1001", "--exchange", "nccl", "--no-burst"])
+    assert "NCCL gather" in line["config"]["exchange"]

@@ -111,10 +111,10 @@ def test_fixed_encoder_loads_reference_checkpoint_format():
         torch.save({"state_dict": ckpt}, path)
         m = make(encoder_path=path)
     assert torch.equal(m.encoder.encoder.encoder[7].weight, sd[p + "7.weight"])
-    # the loaded layers (evaluated through PyTorch, the A/B aid) equal the oracle restatement ...
+    # the loaded layers (evaluated through PyTorch, test-side only) equal the oracle restatement ...
     tiles = torch.rand(3, 32, 32)
     with torch.no_grad():
-        z = m.encoder.forward_torch(tiles)
+        z = m.encoder.fc(m.encoder.encoder(tiles))      # the PyTorch submodules, as the reference evaluates them
     assert torch.allclose(z, osiren.encoder_forward(sd, tiles), atol=1e-6)
     # ... and the product path refuses CPU tensors instead of falling back
     with pytest.raises(RuntimeError):

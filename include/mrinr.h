@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRINR_ABI_VERSION 3
+#define MRINR_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MRINR_API __attribute__((visibility("default")))
@@ -48,6 +48,9 @@ extern "C" {
 #define MRINR_PREC_FP16  0   /* tcgen05 kind::f16, fp16 operands (11-bit significand), fp32 accumulate  -- default */
 #define MRINR_PREC_BF16  1   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate                       */
 #define MRINR_PREC_FP32  2   /* CUDA-core FFMA, fp32 throughout (exact-mode reference kernel)            */
+#define MRINR_PREC_FP16X3 3  /* tcgen05 kind::f16 with split operands (hi + lo fp16 halves of activations and
+                              * weights, three MMAs per product): fp32-class accuracy on the tensor cores for
+                              * weights / modulations too large for an 11-bit significand        */
 
 /* A view of the reference module's parameters (state_dict tensors, fp32, contiguous, on the device).
  * Layout = src/networks/modulated_siren.py: SirenNet (:160-213), Modulator (:304-323), grid (:427-433). */

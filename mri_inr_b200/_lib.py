@@ -16,10 +16,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MRINR_LIB") or os.path.join(_HERE, "lib", "libmrinr.so")
 
 # include/mrinr.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 ACT_SINE, ACT_MORLET = 0, 1
-PREC_FP16, PREC_BF16, PREC_FP32 = 0, 1, 2
-PRECISIONS = {"fp16": PREC_FP16, "bf16": PREC_BF16, "fp32": PREC_FP32}
+PREC_FP16, PREC_BF16, PREC_FP32, PREC_FP16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp16": PREC_FP16, "bf16": PREC_BF16, "fp32": PREC_FP32, "fp16x3": PREC_FP16X3}
 ACTIVATIONS = {"sine": ACT_SINE, "morlet": ACT_MORLET}
 
 # every symbol include/mrinr.h declares (checked by tests/test_abi.py)

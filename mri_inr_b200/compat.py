@@ -52,13 +52,20 @@ def install(gpu_metrics: bool = False) -> None:
     if gpu_metrics:
         from . import error as our_error
 
-        ref_error = importlib.import_module("src.util.error")
-        for name in our_error.__all__:
-            setattr(ref_error, name, getattr(our_error, name))
+        try:
+            ref_error = importlib.import_module("src.util.error")
+        except Exception:
+            # the reference tree (or scikit-image / matplotlib, which its error.py imports) is not there: this package's
+            # module IS src.util.error then (metrics_error + the calculate_* helpers; no visual_error)
+            sys.modules["src.util.error"] = our_error
+            setattr(sys.modules["src.util"], "error", our_error)
+        else:
+            for name in our_error.__all__:
+                setattr(ref_error, name, getattr(our_error, name))
 
 
 def uninstall() -> None:
-    for name in ("src.networks.modulated_siren", "src.util.tiling"):
+    for name in ("src.networks.modulated_siren", "src.util.tiling", "src.util.error"):
         mod = sys.modules.get(name)
         if mod is not None and mod.__name__.startswith("mri_inr_b200."):
             del sys.modules[name]

@@ -49,6 +49,7 @@ extern "C" void mrinr_free_packed(MrinrPacked* p) {
   cudaFree(p->d_net_w16);    // lab
   cudaFree(p->d_net_w16p);   // lab
   cudaFree(p->d_net_w16q);
+  cudaFree(p->d_net_w16x3);
   cudaFree(p->d_layer0);
   cudaFree(p->d_grid);
   cudaFree(p->d_net_bias);
@@ -86,7 +87,8 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
                 "mrinr_pack_weights: siren_patch_size out of range (%d)", v->siren_patch_size);
   MRINR_REQUIRE(v->activation == MRINR_ACT_SINE || v->activation == MRINR_ACT_MORLET, MRINR_E_ARG,
                 "mrinr_pack_weights: unknown activation %d", v->activation);
-  MRINR_REQUIRE(precision == MRINR_PREC_FP16 || precision == MRINR_PREC_BF16 || precision == MRINR_PREC_FP32,
+  MRINR_REQUIRE(precision == MRINR_PREC_FP16 || precision == MRINR_PREC_BF16 || precision == MRINR_PREC_FP32 ||
+                    precision == MRINR_PREC_FP16X3,
                 MRINR_E_ARG, "mrinr_pack_weights: unknown precision %d", precision);
   if (precision != MRINR_PREC_FP32) {
     MRINR_REQUIRE(v->dim_hidden == 256, MRINR_E_UNSUPPORTED,
@@ -144,7 +146,11 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     PK_CUDA(cudaMalloc(&p->d_net_w16, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_w16p, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
 #endif
-    PK_CUDA(cudaMalloc(&p->d_net_w16q, (size_t)(L - 1) * 2 * (H / 8 + 2) * (H / 2) * 8 * sizeof(uint16_t)));
+    const size_t w16q_layer = (size_t)2 * (H / 8 + 2) * (H / 2) * 8;     // elements per layer: [2 ranks][H/8+2][H/2][8]
+    if (precision == MRINR_PREC_FP16 || precision == MRINR_PREC_BF16)
+      PK_CUDA(cudaMalloc(&p->d_net_w16q, (size_t)(L - 1) * w16q_layer * sizeof(uint16_t)));
+    if (precision == MRINR_PREC_FP16X3)
+      PK_CUDA(cudaMalloc(&p->d_net_w16x3, (size_t)(L - 1) * 2 * w16q_layer * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_layer0, (size_t)3 * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_grid, (size_t)C * 2 * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_bias, (size_t)L * H * sizeof(float)));
@@ -186,9 +192,15 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
         PK_RC(run_pack_w16_pair(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
                                 p->d_net_w16p + (size_t)(l - 1) * H * H, st));
 #endif
-        PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], (v->d_net_bias ? v->d_net_bias[l] : nullptr), H,
-                                     precision == MRINR_PREC_BF16,
-                                     p->d_net_w16q + (size_t)(l - 1) * 2 * (H / 8 + 2) * (H / 2) * 8, st));
+        const float* bl = v->d_net_bias ? v->d_net_bias[l] : nullptr;
+        if (precision == MRINR_PREC_FP16X3) {
+          for (int part = 0; part < 2; ++part)
+            PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], bl, H, 0,
+                                         p->d_net_w16x3 + ((size_t)(l - 1) * 2 + part) * w16q_layer, st, part));
+        } else {
+          PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], bl, H, precision == MRINR_PREC_BF16,
+                                       p->d_net_w16q + (size_t)(l - 1) * w16q_layer, st));
+        }
       }
     }
     PK_CUDA(cudaMemcpyAsync(p->d_last_w, v->d_last_weight, H * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -71,6 +71,7 @@ struct MrinrPacked {
   uint16_t* d_net_w16;   // [(L-1)][H/8 (kc)][H (n)][8]  fp16/bf16 UMMA K-major no-swizzle operand layout
   uint16_t* d_net_w16p;  // [(L-1)][2 (rank)][H/8 (kc)][H/2 (n)][8]  same, split by output-row half for cta_group::2
   uint16_t* d_net_w16q;  // [(L-1)][2][H/8 + 2][H/2][8]  pair layout + one K=16 step carrying the bias (hi, lo)
+  uint16_t* d_net_w16x3; // [(L-1)][2 (hi, lo)][2][H/8 + 2][H/2][8]  MRINR_PREC_FP16X3: W = hi + lo, bias step in the hi part
   float*    d_net_bias;  // [L][H]   (zeros when use_bias=False)
   float*    d_layer0;    // [3][H]   W_0[:,0], W_0[:,1], b_0 (layer 0 evaluated in-kernel by the cta_group::2 path)
   float*    d_grid;      // [C][2]   copy of the grid buffer
@@ -104,7 +105,8 @@ int launch_siren_tc(const MrinrPacked* p, const float* d_mods, const int32_t* d_
 int run_transpose(const float* w, int N, int K, float* wT, cudaStream_t st);
 int run_pack_w16(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_t st);
 int run_pack_w16_pair(const float* w, int H, int use_bf16, uint16_t* out, cudaStream_t st);
-int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf16, uint16_t* out, cudaStream_t st);
+int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf16, uint16_t* out, cudaStream_t st,
+                           int part = 0);   // part 1: the fp16 residual w - rn16(w) (zero bias step)
 int run_table16(const float* table, long long n, int use_bf16, uint16_t* out, cudaStream_t st);
 int run_layer0_table(const float* grid, const float* w, const float* b, int C, int H, float w0_initial,
                      int activation, float* table, cudaStream_t st);

@@ -68,7 +68,7 @@ __global__ void pack_w16_pair_kernel(const float* __restrict__ w, int H, int use
 // (b = hi + lo to ~2^-22 relative); the A operand has ones in those two slots, so D = A W^T + b.
 // out is [(2)][34][128][8] = 2 x 69632 bytes per layer.
 __global__ void pack_w16_pair_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias, int H,
-                                          int use_bf16, uint16_t* __restrict__ out) {
+                                          int use_bf16, uint16_t* __restrict__ out, int part) {
   const int per_rank = (H / 8 + 2) * (H / 2) * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * per_rank) return;
@@ -81,7 +81,8 @@ __global__ void pack_w16_pair_bias_kernel(const float* __restrict__ w, const flo
   float v = 0.f;
   if (kc < H / 8) {
     v = w[(long long)n * H + kc * 8 + e];
-  } else if (kc == H / 8 && e < 2 && bias != nullptr) {
+    if (part == 1) v -= __half2float(__float2half_rn(v));      // fp16x3 mode: the residual half of W = hi + lo
+  } else if (part == 0 && kc == H / 8 && e < 2 && bias != nullptr) {
     const float b = bias[n];
     float hi;
     if (use_bf16) hi = __bfloat162float(__float2bfloat16_rn(b)); else hi = __half2float(__float2half_rn(b));
@@ -333,9 +334,10 @@ int run_pack_w16_pair(const float* w, int H, int use_bf16, uint16_t* out, cudaSt
   return check_launch("pack_w16_pair");
 }
 
-int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf16, uint16_t* out, cudaStream_t st) {
+int run_pack_w16_pair_bias(const float* w, const float* bias, int H, int use_bf16, uint16_t* out, cudaStream_t st,
+                           int part) {
   const int n = 2 * (H / 8 + 2) * (H / 2) * 8;
-  pack_w16_pair_bias_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, bias, H, use_bf16, out);
+  pack_w16_pair_bias_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, bias, H, use_bf16, out, part);
   count_launch();
   return check_launch("pack_w16_pair_bias");
 }

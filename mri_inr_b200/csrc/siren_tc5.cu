@@ -23,6 +23,16 @@
 //
 // Everything else is v4: CTA pairs (tcgen05 cta_group::2), two tile slots per CTA (ping-pong), bias through a 17th
 // K step, weights through a 5-slab ring, MMAs issued by a converged warp with elect.sync.
+//
+// Precision modes (template parameter PREC):
+//   MRINR_PREC_FP16 / MRINR_PREC_BF16: one MMA per product, 16-bit operands, fp32 accumulation -- the fast path.
+//   MRINR_PREC_FP16X3: fp32-class accuracy on the tensor cores for weights / modulations large enough that an 11-bit
+//     significand no longer meets the 1e-3 bound (W x 2 with dense modulations).  Activations and weights
+//     are split into hi = rn16(v), lo = rn16(v - hi) and a product is three MMAs, A_hi W_hi + A_lo W_hi + A_hi W_lo
+//     (the dropped lo x lo term is 2^-22 relative), as dense_tc.cu does for the modulator.  The second A operand takes
+//     the shared memory of the second tile slot, so a CTA has ONE tile in flight (no ping-pong: the tensor core waits
+//     for the epilogue) and the weights stream through the ring twice per layer (hi pass incl. the bias step, lo
+//     pass).  The layer-0 table is read from global memory in fp32 instead of living in registers as 16-bit pairs.
 #include "tc_ptx.cuh"
 
 namespace mrinr {
@@ -114,13 +124,15 @@ struct Sched {
   int np;
   int n_full, rem, ksub; // C = 128 n_full + rem; ksub = patches per remainder tile (0 if rem == 0)
   int n_types;           // coordinate blocks per patch: n_full (+ 1 if rem)
-  long long total;       // cluster iterations (4 tiles each)
+  int tpi;               // tiles per cluster iteration: 2 CTAs x tile slots per CTA (4, or 2 in the fp16x3 mode)
+  long long total;       // cluster iterations (tpi tiles each)
 };
 __device__ __forceinline__ int iters_rem(const Sched& s, int n) {   // remainder-block iterations for n patches
-  return s.rem ? ((n + s.ksub - 1) / s.ksub + 3) / 4 : 0;
+  return s.rem ? ((n + s.ksub - 1) / s.ksub + s.tpi - 1) / s.tpi : 0;
 }
-__device__ __forceinline__ Sched make_sched(long long n_act, int C, long long cluster_id, long long n_clusters) {
+__device__ __forceinline__ Sched make_sched(long long n_act, int C, long long cluster_id, long long n_clusters, int tpi) {
   Sched s;
+  s.tpi = tpi;
   s.pa = n_act * cluster_id / n_clusters;
   s.np = (int)(n_act * (cluster_id + 1) / n_clusters - s.pa);
   s.n_full = C / kTileM;
@@ -128,8 +140,8 @@ __device__ __forceinline__ Sched make_sched(long long n_act, int C, long long cl
   s.ksub = s.rem ? (kTileM / s.rem < kMaxSub ? kTileM / s.rem : kMaxSub) : 0;
   s.n_types = s.n_full + (s.rem ? 1 : 0);
   const int blocks = s.np / kSubBlock, tail = s.np - blocks * kSubBlock;
-  s.total = (long long)blocks * (s.n_full * (kSubBlock / 4) + iters_rem(s, kSubBlock));
-  if (tail) s.total += s.n_full * ((tail + 3) / 4) + iters_rem(s, tail);
+  s.total = (long long)blocks * (s.n_full * (kSubBlock / tpi) + iters_rem(s, kSubBlock));
+  if (tail) s.total += s.n_full * ((tail + tpi - 1) / tpi) + iters_rem(s, tail);
   return s;
 }
 struct Walk {          // (sub-block, coordinate block, iteration within the block), advanced without divisions
@@ -140,7 +152,7 @@ struct Walk {          // (sub-block, coordinate block, iteration within the blo
   int itf = 0, itr = 0;
   __device__ __forceinline__ void set_block(const Sched& s) {
     nps = s.np - base < kSubBlock ? s.np - base : kSubBlock;
-    itf = (nps + 3) / 4;
+    itf = (nps + s.tpi - 1) / s.tpi;
     itr = iters_rem(s, nps);
   }
   __device__ __forceinline__ void next(const Sched& s) {
@@ -168,8 +180,13 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
   }
 }
 
-template <int ACT, bool BF16, bool W0ONE>
+template <int ACT, int PREC, bool W0ONE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_tc5_kernel(const SirenTcParams P) {
+  constexpr bool BF16 = (PREC == MRINR_PREC_BF16);
+  constexpr bool X3 = (PREC == MRINR_PREC_FP16X3);   // split operands, three MMAs per product, one tile slot
+  constexpr int kSlots = X3 ? 1 : 2;                 // tiles in flight per CTA
+  constexpr int kPasses = X3 ? 2 : 1;                // trips of a layer's weights through the slab ring
+  constexpr int kTpi = 2 * kSlots;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -190,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
   auto bar = [bar0](int i) -> uint32_t { return bar0 + 8u * (uint32_t)i; };
 
   const long long n_act = P.nactive ? (long long)*P.nactive : P.B;
-  const Sched S = make_sched(n_act, C, blockIdx.x >> 1, gridDim.x >> 1);
+  const Sched S = make_sched(n_act, C, blockIdx.x >> 1, gridDim.x >> 1, kTpi);
   const size_t layer_stride = (size_t)P.B * kH;
 
   // ---- one-time setup ----
@@ -242,7 +259,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     int sub_row = 0;                   // which of the tile's patches this row belongs to (remainder block only)
     int sub_prev = 0;                  // sub_row of the previous iteration's tiles (their output phase runs late)
     bool row_live = false;             // false: padding row of a remainder tile
-    uint32_t T2[kCols / 2];            // layer-0 table of (c_row, this thread's columns), packed pairs
+    uint32_t T2[X3 ? 1 : kCols / 2];   // layer-0 table of (c_row, this thread's columns), packed pairs (not in X3)
+    const float* trow32 = P.table0;    // X3: the fp32 table row of c_row, read per tile
     float* out0 = nullptr; float* out1 = nullptr;      // output element of this row for the tile in slot 0 / 1
 
     auto mod_stage = [&](int slot, uint32_t use) -> float* {
@@ -272,41 +290,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 #pragma unroll
       for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const float4*>(mp + hc * 16 + i * 4);
     };
-    // 16 activations x = pre-activation (bias included) -> h = act(x) * mod, packed to 8 x (2 x 16 bit).
-    // Sine uses the order-pinned pipeline (sines of group g, then multiply + pack of group g-1).
-    auto act16_pack = [&](const uint32_t (&v)[16], const float4 (&m)[4], uint32_t (&pk)[8]) {
-      if (ACT == MRINR_ACT_SINE) {
-        float s[16];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float mg[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x = __uint_as_float(v[g * 4 + i]);
-            s[g * 4 + i] = vsin_live(W0ONE ? x : P.w0 * x, mg[i]);
-          }
-          if (g > 0) {
-            const float4 mm = m[g - 1];
-            pk[(g - 1) * 2 + 0] = vpack2<BF16>(vmul(s[g * 4 - 4], mm.x), vmul(s[g * 4 - 3], mm.y));
-            pk[(g - 1) * 2 + 1] = vpack2<BF16>(vmul(s[g * 4 - 2], mm.z), vmul(s[g * 4 - 1], mm.w));
-          }
-        }
-        pk[6] = vpack2<BF16>(vmul(s[12], m[3].x), vmul(s[13], m[3].y));
-        pk[7] = vpack2<BF16>(vmul(s[14], m[3].z), vmul(s[15], m[3].w));
-      } else {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          pk[g * 2 + 0] = pack2<BF16>(act_fast<ACT, W0ONE>(__uint_as_float(v[g * 4 + 0]), P.w0) * m[g].x,
-                                      act_fast<ACT, W0ONE>(__uint_as_float(v[g * 4 + 1]), P.w0) * m[g].y);
-          pk[g * 2 + 1] = pack2<BF16>(act_fast<ACT, W0ONE>(__uint_as_float(v[g * 4 + 2]), P.w0) * m[g].z,
-                                      act_fast<ACT, W0ONE>(__uint_as_float(v[g * 4 + 3]), P.w0) * m[g].w);
-        }
+    // Four activations h = act(x) * mod of group g -> operand entries: pk = rn16(h); X3 also lo = rn16(h - pk).
+    auto emit4 = [&](int g, float a0, float a1, float a2, float a3, uint32_t (&pk)[8], uint32_t (&lo)[8]) {
+      pk[g * 2 + 0] = vpack2<BF16>(a0, a1);
+      pk[g * 2 + 1] = vpack2<BF16>(a2, a3);
+      if (X3) {
+        float h0, h1, h2, h3;
+        unpack2<false>(pk[g * 2 + 0], h0, h1);
+        unpack2<false>(pk[g * 2 + 1], h2, h3);
+        lo[g * 2 + 0] = pack2<false>(a0 - h0, a1 - h1);
+        lo[g * 2 + 1] = pack2<false>(a2 - h2, a3 - h3);
       }
     };
-    auto store16 = [&](int slot, int hc, const uint32_t (&pk)[8]) {   // columns cg*kCols + hc*16 .. +15 of row t
+    // 16 activations x = pre-activation (bias included) -> h = act(x) * mod, packed to 8 x (2 x 16 bit) (+ 8 residuals).
+    // Order-pinned pipeline: sines of group g (special-function unit), then the FMA-pipe work of group g-1.
+    auto act16_pack = [&](const uint32_t (&v)[16], const float4 (&m)[4], uint32_t (&pk)[8], uint32_t (&lo)[8]) {
+      float s[16];
+      auto finish_group = [&](int g) {
+        const float4 mm = m[g];
+        if (ACT == MRINR_ACT_SINE) {
+          emit4(g, vmul(s[g * 4 + 0], mm.x), vmul(s[g * 4 + 1], mm.y), vmul(s[g * 4 + 2], mm.z), vmul(s[g * 4 + 3], mm.w),
+                pk, lo);
+        } else {
+          // Morlet (modulated_siren.py:80): sin(w0 x) exp(-x^2/2).  One MUFU.SIN per activation as for sine; the
+          // envelope runs on the FMA pipe as packed pairs (gauss2) underneath the next group's sines.
+          const uint64_t h01 = vmul2(gauss2(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1])),
+                                     vmul2(pk2(s[g * 4 + 0], s[g * 4 + 1]), pk2(mm.x, mm.y)));
+          const uint64_t h23 = vmul2(gauss2(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])),
+                                     vmul2(pk2(s[g * 4 + 2], s[g * 4 + 3]), pk2(mm.z, mm.w)));
+          float a0, a1, a2, a3;
+          upk2(h01, a0, a1);
+          upk2(h23, a2, a3);
+          emit4(g, a0, a1, a2, a3, pk, lo);
+        }
+      };
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float mg[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float x = __uint_as_float(v[g * 4 + i]);
+          s[g * 4 + i] = vsin_live(W0ONE ? x : P.w0 * x, mg[i]);
+        }
+        if (g > 0) finish_group(g - 1);
+      }
+      finish_group(3);
+    };
+    // operand entries of columns cg*kCols + hc*16 .. +15 of row t: pk into slot's A buffer; X3: lo into the second one
+    auto store16 = [&](int slot, int hc, const uint32_t (&pk)[8], const uint32_t (&lo)[8]) {
       uint8_t* base = smem + kOffA + slot * 65536 + (cg * (kCols / 8) + hc * 2) * 2048 + t * 16;
       *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(base + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if (X3) {
+        *reinterpret_cast<uint4*>(base + 65536) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(base + 65536 + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
     };
 
     // output phase of a finished tile: y = sin(w0 (h_{L-1} . w_last + b_last)), h_{L-1} = act(D) * mod_{L-1}.
@@ -330,6 +368,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       uint32_t va[16], vb[16];
       tmem_ld16(tcol, va);
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      uint64_t d01 = 0ull, d23 = 0ull;             // Morlet: packed pairs of partial dots
       auto dot16 = [&](const uint32_t (&v)[16], int hc) {
         float4 mw[4];
         load4x4(mp, hc, mw);
@@ -337,18 +376,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         for (int g = 0; g < 4; ++g) {
           const float x0 = __uint_as_float(v[g * 4 + 0]), x1 = __uint_as_float(v[g * 4 + 1]);
           const float x2 = __uint_as_float(v[g * 4 + 2]), x3 = __uint_as_float(v[g * 4 + 3]);
-          float h0, h1, h2, h3;
+          const float h0 = vsin_live(W0ONE ? x0 : P.w0 * x0, mw[g].x), h1 = vsin_live(W0ONE ? x1 : P.w0 * x1, mw[g].y);
+          const float h2 = vsin_live(W0ONE ? x2 : P.w0 * x2, mw[g].z), h3 = vsin_live(W0ONE ? x3 : P.w0 * x3, mw[g].w);
           if (ACT == MRINR_ACT_SINE) {
-            h0 = vsin_live(W0ONE ? x0 : P.w0 * x0, mw[g].x); h1 = vsin_live(W0ONE ? x1 : P.w0 * x1, mw[g].y);
-            h2 = vsin_live(W0ONE ? x2 : P.w0 * x2, mw[g].z); h3 = vsin_live(W0ONE ? x3 : P.w0 * x3, mw[g].w);
+            d0 = fmaf(h0, mw[g].x, d0);
+            d1 = fmaf(h1, mw[g].y, d1);
+            d2 = fmaf(h2, mw[g].z, d2);
+            d3 = fmaf(h3, mw[g].w, d3);
           } else {
-            h0 = act_fast<ACT, W0ONE>(x0, P.w0); h1 = act_fast<ACT, W0ONE>(x1, P.w0);
-            h2 = act_fast<ACT, W0ONE>(x2, P.w0); h3 = act_fast<ACT, W0ONE>(x3, P.w0);
+            d01 = vfma2(vmul2(gauss2(x0, x1), pk2(h0, h1)), pk2(mw[g].x, mw[g].y), d01);
+            d23 = vfma2(vmul2(gauss2(x2, x3), pk2(h2, h3)), pk2(mw[g].z, mw[g].w), d23);
           }
-          d0 = fmaf(h0, mw[g].x, d0);
-          d1 = fmaf(h1, mw[g].y, d1);
-          d2 = fmaf(h2, mw[g].z, d2);
-          d3 = fmaf(h3, mw[g].w, d3);
         }
       };
 #pragma unroll 1
@@ -363,6 +401,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       TL(1020 + slot);
       tc_fence_before();
       finish_phase(slot, use, false);
+      if (ACT != MRINR_ACT_SINE) {
+        upk2(d01, d0, d1);
+        upk2(d23, d2, d3);
+      }
       float dot = (d0 + d1) + (d2 + d3);
       // combine the column groups of a row: groups 1.. hand their partial dot to group 0's warp of the same quarter
       float* part = s_part + slot * 3 * kTileM;
@@ -399,17 +441,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           sub_row = row_live ? sub : 0;
           c_row = S.n_full * kTileM + (row_live ? t - sub * S.rem : 0);
         }
-        const float4* trow = reinterpret_cast<const float4*>(P.table0 + (size_t)c_row * kH + cg * kCols);
+        trow32 = P.table0 + (size_t)c_row * kH + cg * kCols;
+        if (!X3) {
+          const float4* trow = reinterpret_cast<const float4*>(trow32);
 #pragma unroll
-        for (int i = 0; i < kCols / 4; ++i) {
-          const float4 v = __ldg(trow + i);
-          T2[i * 2 + 0] = pack2<BF16>(v.x, v.y);
-          T2[i * 2 + 1] = pack2<BF16>(v.z, v.w);
+          for (int i = 0; i < kCols / 4; ++i) {
+            const float4 v = __ldg(trow + i);
+            T2[i * 2 + 0] = pack2<BF16>(v.x, v.y);
+            T2[i * 2 + 1] = pack2<BF16>(v.z, v.w);
+          }
         }
       }
       // ---- per slot: finish the previous tile of the slot, then write the layer-0 operand of the new one ----
 #pragma unroll 1
-      for (int slot = 0; slot < 2; ++slot) {
+      for (int slot = 0; slot < kSlots; ++slot) {
         TL(910 + slot);
         const uint32_t ok0 = last ? 1u : peek_mods(slot, use0);
         TL(920 + slot);
@@ -417,7 +462,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         if (last) continue;
         {
           // which patch does this row belong to?  (a phantom tile / padding row has no output)
-          const int ti = w.j * 4 + slot * 2 + (int)rank;
+          const int ti = w.j * kTpi + slot * 2 + (int)rank;
           const int pl = cur_type < S.n_full ? ti : ti * S.ksub + sub_row;
           float* o = nullptr;
           if (row_live && pl < w.nps) {
@@ -431,20 +476,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         if (!ok0) wait_mods(slot, use0);
         const float* mp = mod_stage(slot, use0) + sub_row * kH + cg * kCols;
         TL(2005 + slot);
+        if (!X3) {
 #pragma unroll
-        for (int hc = 0; hc < kCols / 16; ++hc) {
-          float4 m[4];
-          load4x4(mp, hc, m);
-          uint32_t pk[8];
+          for (int hc = 0; hc < kCols / 16; ++hc) {
+            float4 m[4];
+            load4x4(mp, hc, m);
+            uint32_t pk[8], lo[8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float a0, a1, a2, a3;
-            unpack2<BF16>(T2[hc * 8 + g * 2 + 0], a0, a1);
-            unpack2<BF16>(T2[hc * 8 + g * 2 + 1], a2, a3);
-            pk[g * 2 + 0] = pack2<BF16>(a0 * m[g].x, a1 * m[g].y);
-            pk[g * 2 + 1] = pack2<BF16>(a2 * m[g].z, a3 * m[g].w);
+            for (int g = 0; g < 4; ++g) {
+              float a0, a1, a2, a3;
+              unpack2<BF16>(T2[hc * 8 + g * 2 + 0], a0, a1);
+              unpack2<BF16>(T2[hc * 8 + g * 2 + 1], a2, a3);
+              pk[g * 2 + 0] = pack2<BF16>(a0 * m[g].x, a1 * m[g].y);
+              pk[g * 2 + 1] = pack2<BF16>(a2 * m[g].z, a3 * m[g].w);
+            }
+            store16(slot, hc, pk, lo);
           }
-          store16(slot, hc, pk);
+        } else {
+          // X3: the table in full precision, straight from global memory (L2-resident: 590 KB shared by all CTAs)
+#pragma unroll 2
+          for (int hc = 0; hc < kCols / 16; ++hc) {
+            float4 m[4];
+            load4x4(mp, hc, m);
+            uint32_t pk[8], lo[8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 tv = __ldg(reinterpret_cast<const float4*>(trow32 + hc * 16 + g * 4));
+              emit4(g, tv.x * m[g].x, tv.y * m[g].y, tv.z * m[g].z, tv.w * m[g].w, pk, lo);
+            }
+            store16(slot, hc, pk, lo);
+          }
         }
         finish_phase(slot, use0, true);
         TL(2010 + slot);
@@ -456,7 +517,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         const uint32_t ev = ev0 + (uint32_t)(l - 1);
         const uint32_t use = use0 + (uint32_t)l;
 #pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int slot = 0; slot < kSlots; ++slot) {
           const uint32_t tcol = taddr_row + (uint32_t)slot * 256u + (uint32_t)(cg * kCols);
           TL(3000 + l * 10 + slot);
           const uint32_t okm = peek_mods(slot, use);
@@ -470,17 +531,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 #pragma unroll 1
           for (int hp = 0; hp < kPairs; ++hp) {
             float4 m[4];
-            uint32_t pk[8];
+            uint32_t pk[8], lo[8];
             tmem_ld_wait();
             tmem_ld16(tcol + (uint32_t)(hp * 2 + 1) * 16u, vb);     // next chunk lands while this one is processed
             load4x4(mp, hp * 2, m);
-            act16_pack(va, m, pk);
-            store16(slot, hp * 2, pk);
+            act16_pack(va, m, pk, lo);
+            store16(slot, hp * 2, pk, lo);
             tmem_ld_wait();
             if (hp < kPairs - 1) tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
             load4x4(mp, hp * 2 + 1, m);
-            act16_pack(vb, m, pk);
-            store16(slot, hp * 2 + 1, pk);
+            act16_pack(vb, m, pk, lo);
+            store16(slot, hp * 2 + 1, pk, lo);
           }
           tc_fence_before();
           finish_phase(slot, use, true);
@@ -508,38 +569,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           // not unrolled over the slots: the issuer shares its sub-partition's instruction cache with two epilogue
           // warps, and 12 KB of straight-line issue code evicted their loops at every phase change
 #pragma unroll 1
-          for (int slot = 0; slot < 2; ++slot) {
+          for (int slot = 0; slot < kSlots; ++slot) {
             const uint32_t a_lo = a_lo0 + (uint32_t)slot * (65536u >> 4);
+            const uint32_t a2_lo = a_lo0 + (65536u >> 4);      // X3: the residual operand A_lo lives in the second buffer
             const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
             TL(6000 + l * 10 + slot);
             mbar_wait_backoff(bar(kBarAFull + slot), ev & 1u, P.errflag, 1, 32);
             TL(7000 + l * 10 + slot);
+#pragma unroll 1
+            for (int pass = 0; pass < kPasses; ++pass) {
+              const uint32_t wev = ev * (uint32_t)kPasses + (uint32_t)pass;     // trips of the slab ring so far
 #pragma unroll
-            for (int s = 0; s < kNumSlabs; ++s) {
-              if (slot == 0) {
-                mbar_wait_backoff(bar(kBarWFull + s), ev & 1u, P.errflag, 2, 32);
-                mbar_wait_backoff(bar(kBarWPeer + s), ev & 1u, P.errflag, 8, 32);
-              }
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t b_lo = b_lo0 + (uint32_t)s * (kSlabBytes >> 4);
-#ifndef MRINR_POWER_NO_MMA     // tools/power_split.py only: wrong results, the tensor core stays idle
-                if (s < 4) {
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk)
-                    umma_f16_pair_lohi(d_tmem, a_lo + (uint32_t)(s * 4 + kk) * 256u, b_lo + (uint32_t)kk * 256u, desc_hi,
-                                       idesc, (s | kk) != 0 ? 1u : 0u);
-                } else {
-                  umma_f16_pair_lohi(d_tmem, ones_lo, b_lo, desc_hi, idesc, 1u);      // + bias
+              for (int s = 0; s < kNumSlabs; ++s) {
+                if (slot == 0) {
+                  mbar_wait_backoff(bar(kBarWFull + s), wev & 1u, P.errflag, 2, 32);
+                  mbar_wait_backoff(bar(kBarWPeer + s), wev & 1u, P.errflag, 8, 32);
                 }
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint32_t b_lo = b_lo0 + (uint32_t)s * (kSlabBytes >> 4);
+#ifndef MRINR_POWER_NO_MMA     // tools/power_split.py only: wrong results, the tensor core stays idle
+                  if (s < 4) {
+                    if (pass == 0) {
+#pragma unroll
+                      for (int kk = 0; kk < 4; ++kk)           // A (X3: A_hi) x W (X3: W_hi)
+                        umma_f16_pair_lohi(d_tmem, a_lo + (uint32_t)(s * 4 + kk) * 256u, b_lo + (uint32_t)kk * 256u,
+                                           desc_hi, idesc, (s | kk) != 0 ? 1u : 0u);
+                      if (X3) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)         // A_lo x W_hi
+                          umma_f16_pair_lohi(d_tmem, a2_lo + (uint32_t)(s * 4 + kk) * 256u, b_lo + (uint32_t)kk * 256u,
+                                             desc_hi, idesc, 1u);
+                      }
+                    } else {
+#pragma unroll
+                      for (int kk = 0; kk < 4; ++kk)           // A_hi x W_lo
+                        umma_f16_pair_lohi(d_tmem, a_lo + (uint32_t)(s * 4 + kk) * 256u, b_lo + (uint32_t)kk * 256u,
+                                           desc_hi, idesc, 1u);
+                    }
+                  } else if (pass == 0) {
+                    umma_f16_pair_lohi(d_tmem, ones_lo, b_lo, desc_hi, idesc, 1u);      // + bias
+                  }
 #endif
-                // slot 1 is the second and last user of a slab: hand every slab back as soon as its MMAs are issued, so
-                // that the next layer's weights stream in underneath this layer's remaining MMAs (one commit per slab
-                // either way; with a single hand-back at the end of the layer the ~1500-cycle L2 round trip of the
-                // reload sat between MMA(l, slot 1) and MMA(l+1, slot 0))
-                if (slot == 1) umma_commit_pair(bar(kBarWEmpty + s), 3);
+                  // The last slot is the last user of a slab: hand every slab back as soon as its MMAs are issued, so
+                  // that the next weights stream in underneath the remaining MMAs (one commit per slab either way;
+                  // with a single hand-back at the end of the layer the ~1500-cycle L2 round trip of the reload sat
+                  // between MMA(l, slot 1) and MMA(l+1, slot 0))
+                  if (slot == kSlots - 1) umma_commit_pair(bar(kBarWEmpty + s), 3);
+                }
+                __syncwarp();
               }
-              __syncwarp();
             }
             if (elect_one()) umma_commit_pair(bar(kBarAccFull + slot), 3);
             __syncwarp();
@@ -549,14 +628,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       }
     } else if (lane == 0) {
       // =========================== forwarder (peer CTA): my slab has landed ===========================
-      uint32_t ev = 0;
-      for (long long it = 0; it < S.total; ++it) {
-        for (int l = 1; l < L; ++l, ++ev) {
+      const long long n_trips = S.total * (long long)(L - 1) * kPasses;     // trips of the slab ring
+      for (long long wev = 0; wev < n_trips; ++wev) {
 #pragma unroll 1
-          for (int s = 0; s < kNumSlabs; ++s) {
-            mbar_wait_backoff(bar(kBarWFull + s), ev & 1u, P.errflag, 9);
-            mbar_arrive_cluster(bar(kBarWPeer + s), 0);
-          }
+        for (int s = 0; s < kNumSlabs; ++s) {
+          mbar_wait_backoff(bar(kBarWFull + s), (uint32_t)wev & 1u, P.errflag, 9);
+          mbar_arrive_cluster(bar(kBarWPeer + s), 0);
         }
       }
     }
@@ -583,10 +660,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         const bool full = ww.type < S.n_full;
         const int ns = full ? 1 : S.ksub;
 #pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int slot = 0; slot < kSlots; ++slot) {
           const uint32_t full_bar = bar(kBarModFull + slot * kModStages + stage);
           mbar_wait_backoff(bar(kBarModEmpty + slot * kModStages + stage), ((use / kModStages) & 1u) ^ 1u, P.errflag, 10);
-          const int ti = ww.j * 4 + slot * 2 + (int)rank;
+          const int ti = ww.j * kTpi + slot * 2 + (int)rank;
 #pragma unroll 1
           for (int sidx = 0; sidx < ns; ++sidx) {
             int pl = full ? ti : ti * S.ksub + sidx;
@@ -613,16 +690,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         for (int l = 1; l < L; ++l, ++ev) {
           issue_mods_of(it, l, w);
           if (l == l_early && it + 1 < S.total) issue_mods_of(it + 1, 0, wn);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(P.w16q) + ((size_t)(l - 1) * 2 + rank) * kLayerBytes;
 #pragma unroll 1
-          for (int sl = 0; sl < kNumSlabs; ++sl) {
-            const uint32_t bytes = sl < 4 ? kSlabBytes : kBiasSlabBytes;
-            mbar_wait_backoff(bar(kBarWEmpty + sl), (ev & 1u) ^ 1u, P.errflag, 7);
-            if (elect_one()) {
-              mbar_expect_tx(bar(kBarWFull + sl), bytes);
-              bulk_g2s(sW + sl * kSlabBytes, src + (size_t)sl * kSlabBytes, bytes, bar(kBarWFull + sl));
+          for (int pass = 0; pass < kPasses; ++pass) {
+            // X3: [(L-1)][hi pass, lo pass][rank]; otherwise [(L-1)][rank]
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(X3 ? P.w16x3 : P.w16q) +
+                                 (((size_t)(l - 1) * kPasses + pass) * 2 + rank) * kLayerBytes;
+            const uint32_t wev = ev * (uint32_t)kPasses + (uint32_t)pass;
+#pragma unroll 1
+            for (int sl = 0; sl < kNumSlabs; ++sl) {
+              const uint32_t bytes = sl < 4 ? kSlabBytes : kBiasSlabBytes;
+              mbar_wait_backoff(bar(kBarWEmpty + sl), (wev & 1u) ^ 1u, P.errflag, 7);
+              if (elect_one()) {
+                mbar_expect_tx(bar(kBarWFull + sl), bytes);
+                bulk_g2s(sW + sl * kSlabBytes, src + (size_t)sl * kSlabBytes, bytes, bar(kBarWFull + sl));
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
         }
         w = wn;
@@ -640,43 +723,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
   if (warp == kEpiWarps) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
-template <int ACT, bool BF16, bool W0ONE>
+template <int ACT, int PREC, bool W0ONE>
 static int launch_one(const SirenTcParams& P, int grid, cudaStream_t st) {
-  MRINR_SMEM_OPT_IN((siren_tc5_kernel<ACT, BF16, W0ONE>), kSmemBytes);
-  siren_tc5_kernel<ACT, BF16, W0ONE><<<grid, kThreads, kSmemBytes, st>>>(P);
+  MRINR_SMEM_OPT_IN((siren_tc5_kernel<ACT, PREC, W0ONE>), kSmemBytes);
+  siren_tc5_kernel<ACT, PREC, W0ONE><<<grid, kThreads, kSmemBytes, st>>>(P);
   count_launch();
   return check_launch("siren_tc5");
+}
+
+template <int ACT, int PREC>
+static int launch_w0(const SirenTcParams& P, int grid, bool w0one, cudaStream_t st) {
+  return w0one ? launch_one<ACT, PREC, true>(P, grid, st) : launch_one<ACT, PREC, false>(P, grid, st);
 }
 
 int launch_siren_tc_v5(const MrinrPacked* p, const float* d_mods, const int32_t* d_idx, const int32_t* d_nactive,
                        int64_t B, float* d_out, cudaStream_t st) {
   MRINR_REQUIRE(p->H == kH && p->L <= kMaxLayers && p->L >= 3 && p->C >= kTileM, MRINR_E_UNSUPPORTED,
-                "siren_tc5: unsupported configuration (H=%d L=%d C=%d)", p->H, p->L, p->C);
+                "siren_tc5: the tensor-core path needs dim_hidden 256, 3 <= num_layers <= 16 and siren_patch_size^2 >= "
+                "128 (got H=%d L=%d C=%d); use MRINR_PREC_FP32", p->H, p->L, p->C);
+  const bool x3 = (p->precision == MRINR_PREC_FP16X3);
+  MRINR_REQUIRE(x3 ? p->d_net_w16x3 != nullptr : p->d_net_w16q != nullptr, MRINR_E_ARG,
+                "siren_tc5: the weights were not packed for precision mode %d", p->precision);
   SirenTcParams P;
-  P.table0 = p->d_table0; P.w16 = p->d_net_w16; P.w16p = p->d_net_w16p; P.w16q = p->d_net_w16q;
+  P.table0 = p->d_table0; P.table16 = p->d_table16; P.w16 = p->d_net_w16; P.w16p = p->d_net_w16p;
+  P.w16q = p->d_net_w16q; P.w16x3 = p->d_net_w16x3;
   P.layer0 = p->d_layer0; P.grid = p->d_grid; P.w0_initial = p->w0_initial;
   P.bias = p->d_net_bias; P.last_w = p->d_last_w;
   P.last_b = p->d_last_b; P.mods = d_mods; P.idx = d_idx; P.nactive = d_nactive; P.out = d_out;
   P.errflag = p->d_errflag; P.B = B; P.C = p->C; P.L = p->L; P.w0 = p->w0;
-  // one cluster per SM pair, but never more clusters than there are groups of 4 patches (a cluster iteration
-  // processes 4 tiles of the same coordinate block)
+  // one cluster per SM pair, but never more clusters than there are groups of tiles-per-iteration patches (a cluster
+  // iteration processes 4 tiles -- 2 in the fp16x3 mode -- of the same coordinate block)
+  const long long tpi = x3 ? 2 : 4;
   long long clusters = p->num_sms / 2;
-  const long long groups = (B + 3) / 4;
+  const long long groups = (B + tpi - 1) / tpi;
   if (clusters > groups) clusters = groups;
   if (clusters < 1) clusters = 1;
   const int grid = (int)(clusters * 2);
   const bool w0one = (p->w0 == 1.0f);
-  const bool bf16 = (p->precision == MRINR_PREC_BF16);
   const bool morlet = (p->activation == MRINR_ACT_MORLET);
-#define MRINR_TC_CASE(A, Bf, W) return launch_one<A, Bf, W>(P, grid, st)
-  if (!morlet) {
-    if (!bf16) { if (w0one) MRINR_TC_CASE(MRINR_ACT_SINE, false, true); else MRINR_TC_CASE(MRINR_ACT_SINE, false, false); }
-    else       { if (w0one) MRINR_TC_CASE(MRINR_ACT_SINE, true, true);  else MRINR_TC_CASE(MRINR_ACT_SINE, true, false); }
-  } else {
-    if (!bf16) { if (w0one) MRINR_TC_CASE(MRINR_ACT_MORLET, false, true); else MRINR_TC_CASE(MRINR_ACT_MORLET, false, false); }
-    else       { if (w0one) MRINR_TC_CASE(MRINR_ACT_MORLET, true, true);  else MRINR_TC_CASE(MRINR_ACT_MORLET, true, false); }
+  switch (p->precision) {
+    case MRINR_PREC_FP16:
+      return morlet ? launch_w0<MRINR_ACT_MORLET, MRINR_PREC_FP16>(P, grid, w0one, st)
+                    : launch_w0<MRINR_ACT_SINE, MRINR_PREC_FP16>(P, grid, w0one, st);
+    case MRINR_PREC_BF16:
+      return morlet ? launch_w0<MRINR_ACT_MORLET, MRINR_PREC_BF16>(P, grid, w0one, st)
+                    : launch_w0<MRINR_ACT_SINE, MRINR_PREC_BF16>(P, grid, w0one, st);
+    case MRINR_PREC_FP16X3:
+      return morlet ? launch_w0<MRINR_ACT_MORLET, MRINR_PREC_FP16X3>(P, grid, w0one, st)
+                    : launch_w0<MRINR_ACT_SINE, MRINR_PREC_FP16X3>(P, grid, w0one, st);
+    default:
+      break;
   }
-#undef MRINR_TC_CASE
+  set_error("siren_tc5: precision mode %d is not a tensor-core mode", p->precision);
+  return MRINR_E_ARG;
 }
 
 }  // namespace v5

@@ -335,6 +335,66 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
+// ---- packed fp32 pairs (FMUL2 / FFMA2 / FADD2: one instruction, two lanes of work) ---------------------------
+// The arithmetic wrappers are volatile (part of the order-pinned epilogue, see above); the pack / unpack moves are not,
+// so that the compiler can keep constants and register pairs wherever it likes.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t vmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm volatile("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t vadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm volatile("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t vsub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm volatile("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t vfma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// Morlet envelope exp(-x^2/2) (modulated_siren.py:80) for two pre-activations, on the FMA pipe: the special-function
+// unit already evaluates one sine per activation and is the epilogue's bottleneck (16 results/clk/SM); a second MUFU
+// op per activation (ex2.approx) doubled the hidden phases.  2^y with y = -x^2 log2(e)/2: round-to-integer by the
+// magic-number trick, degree-4 polynomial of the fraction in [-0.5, 0.5] (relative error 2.6e-6; coefficients fitted
+// for minimal relative error, checked in tests/test_host_logic.py), exponent added with an integer shift-add.
+// x^2 is clamped at 174 (|x| > 13.2 -> ~1e-38 instead of a wrapped exponent).
+__device__ __forceinline__ uint64_t gauss2(float x0, float x1) {
+  const uint64_t X = pk2(x0, x1);
+  float t0, t1;
+  upk2(vmul2(X, X), t0, t1);
+  t0 = fminf(t0, 174.0f);
+  t1 = fminf(t1, 174.0f);
+  const uint64_t T = pk2(t0, t1);
+  const uint64_t NEGC = 0xBF38AA3BBF38AA3BULL;                     // -log2(e)/2, twice
+  const uint64_t Z = vfma2(T, NEGC, 0x4B4000004B400000ULL);        // + 1.5 * 2^23: round(y) in the low mantissa bits
+  const uint64_t NNEG = vsub2(0x4B4000004B400000ULL, Z);           // -n, n = round(y)
+  const uint64_t F = vfma2(T, NEGC, NNEG);                         // y - n  in [-0.5, 0.5]
+  uint64_t Pp = vfma2(0x3C1CCBEA3C1CCBEAULL, F, 0x3D650A203D650A20ULL);
+  Pp = vfma2(Pp, F, 0x3E76036D3E76036DULL);
+  Pp = vfma2(Pp, F, 0x3F31706E3F31706EULL);
+  Pp = vfma2(Pp, F, 0x3F7FFFF43F7FFFF4ULL);
+  float p0, p1, z0, z1;
+  upk2(Pp, p0, p1);
+  upk2(Z, z0, z1);
+  const float g0 = __int_as_float(__float_as_int(p0) + (__float_as_int(z0) << 23));
+  const float g1 = __int_as_float(__float_as_int(p1) + (__float_as_int(z1) << 23));
+  return pk2(g0, g1);
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct SirenTcParams {
@@ -343,6 +403,7 @@ struct SirenTcParams {
   const uint16_t* w16;      // [(L-1)][32][256][8]
   const uint16_t* w16p;     // [(L-1)][2][32][128][8]   (cta_group::2 path)
   const uint16_t* w16q;     // [(L-1)][2][34][128][8]   (cta_group::2 path, bias carried by a 17th K step)
+  const uint16_t* w16x3;    // [(L-1)][2 (hi pass, lo pass)][2][34][128][8]   fp16x3 mode: W = hi + lo
   const float* layer0;      // [3][256]  W_0[:,0], W_0[:,1], b_0
   const float* grid;        // [C][2]
   float w0_initial;

@@ -165,9 +165,22 @@ class Encoder(nn.Module):
 class ModulatedSiren(nn.Module):
     """Drop-in for ``src.networks.modulated_siren.ModulatedSiren``.
 
-    Extra (non-reference) attribute: ``precision`` in {"fp16" (default), "bf16", "fp32"} -- operand format of
-    the hidden-layer tensor-core contractions; "fp32" selects the exact CUDA-core kernel.  The default can be
-    set with the environment variable ``MRINR_PRECISION``."""
+    Extra (non-reference) attribute: ``precision`` -- arithmetic of the hidden-layer contractions:
+
+    * ``"fp16"`` (default): tcgen05, fp16 operands (11-bit significand), fp32 accumulation -- the fast path;
+    * ``"bf16"``: the same with bf16 operands (meets 1e-3 only for random-init-scale weights, SURVEY H2);
+    * ``"fp16x3"``: tcgen05 with split operands (hi + lo fp16 halves of activations and weights, three MMAs per
+      product): fp32-class accuracy for weight / modulation scales where an 11-bit significand no longer meets the
+      1e-3 bound;
+    * ``"fp32"``: the exact CUDA-core kernel;
+    * ``"auto"``: the cheapest of fp16 -> fp16x3 -> fp32 whose output agrees with the fp32 kernel to
+      ``AUTO_TOLERANCE`` on a sample of the first batch (a one-off self-check per set of weights; the choice is
+      kept in ``precision_selected`` until the parameters change).
+
+    The default can be set with the environment variable ``MRINR_PRECISION``."""
+
+    AUTO_TOLERANCE = 2.5e-4      # max-abs against the fp32 kernel: a factor 4 under north_star's 1e-3
+    AUTO_SAMPLE = 256            # patches of the first batch used by the self-check
 
     def __init__(self, dim_in, dim_hidden, dim_out, num_layers, latent_dim, w0, w0_initial, use_bias, dropout,
                  modulate, encoder_type, encoder_path, outer_patch_size, inner_patch_size, siren_patch_size, device,
@@ -195,6 +208,8 @@ class ModulatedSiren(nn.Module):
         self.encoder._owner = weakref.ref(self)
         self._pack_key = None
         self._pack = None
+        self.precision_selected = None      # the mode "auto" resolved to (else the mode in use)
+        self._auto_key = None
 
     # ---- packed weights: derived state, rebuilt when parameters change (load_state_dict, .to(), optimizer step)
     def _pack_tensors(self) -> Sequence[Optional[torch.Tensor]]:
@@ -207,27 +222,71 @@ class ModulatedSiren(nn.Module):
         ts += self.encoder.params()
         return ts
 
+    def _weights_key(self):
+        return (self.activation,) + tuple(
+            (None if t is None else (t.data_ptr(), t._version, str(t.device))) for t in self._pack_tensors())
+
+    def _effective_precision(self) -> str:
+        if self.precision != "auto":
+            self.precision_selected = self.precision
+            return self.precision
+        if self._auto_key != self._weights_key():
+            # not resolved yet for these weights: the fast mode, until synthesize() has seen data to check it on
+            self.precision_selected = None
+            return "fp16"
+        return self.precision_selected
+
     def _packed(self) -> ops.PackedWeights:
-        ts = self._pack_tensors()
-        key = (self.precision, self.activation) + tuple(
-            (None if t is None else (t.data_ptr(), t._version, str(t.device))) for t in ts)
+        return self._packed_as(self._effective_precision())
+
+    def _build_pack(self, precision: str) -> ops.PackedWeights:
+        return ops.PackedWeights(
+            grid=self.grid,
+            net_weights=[l.weight for l in self.net.layers],
+            net_biases=[l.bias for l in self.net.layers],
+            last_weight=self.net.last_layer.weight, last_bias=self.net.last_layer.bias,
+            mod_weights=[s[0].weight for s in self.modulator.layers],
+            mod_biases=[s[0].bias for s in self.modulator.layers],
+            w0=self.net.w0, w0_initial=self.net.w0_initial, activation=self.activation,
+            precision=precision, siren_patch_size=self.siren_patch_size,
+            encoder_params=self.encoder.params(),
+            outer_patch_size=self.outer_patch_size)
+
+    def _resolve_auto(self, mods: torch.Tensor) -> None:
+        """One-off self-check of ``precision="auto"``: evaluate a strided sample of the batch's modulations in every
+        tensor-core mode and keep the cheapest one that agrees with the fp32 kernel to ``AUTO_TOLERANCE``."""
+        B = mods.shape[1]
+        n = min(B, self.AUTO_SAMPLE)
+        sel = torch.linspace(0, B - 1, n, device=mods.device).round().long()
+        sample = mods[:, sel].contiguous()
+        exact_pack = self._build_pack("fp32")
+        try:
+            exact = ops.siren_forward(exact_pack, sample)
+            chosen, self.auto_errors = "fp32", {}
+            for mode in ("fp16", "fp16x3"):
+                pack = self._build_pack(mode)
+                try:
+                    err = float((ops.siren_forward(pack, sample) - exact).abs().max())
+                finally:
+                    pack.free()
+                self.auto_errors[mode] = err
+                if err <= self.AUTO_TOLERANCE:
+                    chosen = mode
+                    break
+        finally:
+            exact_pack.free()
+        self.precision_selected = chosen
+        self._auto_key = self._weights_key()
+
+    def _packed_as(self, precision: str) -> ops.PackedWeights:
+        key = (precision,) + self._weights_key()
         if self._pack is None or key != self._pack_key:
             if not self.grid.is_cuda:
                 raise RuntimeError("mri_inr_b200.ModulatedSiren runs on CUDA only: call .to('cuda') first "
                                    "(there is no CPU fallback)")
             if self._pack is not None:
                 self._pack.free()
-            self._pack = ops.PackedWeights(
-                grid=self.grid,
-                net_weights=[l.weight for l in self.net.layers],
-                net_biases=[l.bias for l in self.net.layers],
-                last_weight=self.net.last_layer.weight, last_bias=self.net.last_layer.bias,
-                mod_weights=[s[0].weight for s in self.modulator.layers],
-                mod_biases=[s[0].bias for s in self.modulator.layers],
-                w0=self.net.w0, w0_initial=self.net.w0_initial, activation=self.activation,
-                precision=self.precision, siren_patch_size=self.siren_patch_size,
-                encoder_params=self.encoder.params(),
-                outer_patch_size=self.outer_patch_size)
+            self._pack = self._build_pack(precision)
             self._pack_key = key
         return self._pack
 
@@ -250,6 +309,8 @@ class ModulatedSiren(nn.Module):
                    out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``self.net(coords, mods)`` over the module's grid (modulated_siren.py:448-455) -> ``[B,S,S]``."""
         s = self.siren_patch_size
+        if self.precision == "auto" and self._auto_key != self._weights_key() and mods.shape[1] > 0:
+            self._resolve_auto(mods)
         y = ops.siren_forward(self._packed(), mods, black=black, out=out, workspace=workspace)
         return y.view(-1, s, s)
 

@@ -63,10 +63,18 @@ class ReconstructionPipeline:
         nV, nH, P, O, I, S = geom
         n = images.shape[0]
         B = n * P
+        if m.precision == "auto":
+            packed = m._packed()        # the handle is rebuilt when the self-check below changes the mode
         patches, _, black = ops.image_to_patches(images, O, I, with_black_mask=skip_black, out=bufs["patches"][:B])
         z = m.encoder(patches, workspace=bufs["enc_ws"])
         mods = ops.modulator_forward(packed, z.contiguous(),
                                      out=bufs["mods"][: packed.L * B * packed.H].view(packed.L, B, packed.H))
+        if m.precision == "auto":
+            # precision="auto": the first chunk's modulations decide the mode (one-off self-check against the fp32
+            # kernel, ModulatedSiren._resolve_auto); the handle may have been rebuilt, so fetch it again
+            if m._auto_key != m._weights_key():
+                m._resolve_auto(mods)
+            packed = m._packed()
         if kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

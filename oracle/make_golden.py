@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import ref_import, siren
-from .synth import MODEL_CASES, synth_image, synth_tiles
+from .synth import HARD_CASES, MODEL_CASES, synth_image, synth_tiles
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -37,7 +37,7 @@ def main() -> None:
 
     # ---- model forward (modulated_siren.py:435-457) with strictly loaded synthetic state_dicts
     out = {}
-    for name, sd_kw, act, model_kw in MODEL_CASES:
+    for name, sd_kw, act, model_kw in MODEL_CASES + HARD_CASES:
         sd = siren.synth_state_dict(**sd_kw)
         model = ref_import.build_reference_model(activation=act, **model_kw)
         missing = model.load_state_dict(sd, strict=True)

@@ -46,3 +46,24 @@ def ssim(original: np.ndarray, predicted: np.ndarray, win_size: int = 7, k1: flo
     s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
     pad = (win_size - 1) // 2
     return float(s[pad:-pad, pad:-pad].mean())
+
+
+def ssim_direct(original: np.ndarray, predicted: np.ndarray, win_size: int = 7, k1: float = 0.01, k2: float = 0.03) -> float:
+    """A second, independent formulation of the same SSIM: every win x win window is materialised
+    (``sliding_window_view``) and its sample mean / variance / covariance are computed directly from centred values in
+    fp64 -- no uniform filter, no ``E[x^2] - E[x]^2`` difference, no border handling (only windows fully inside the
+    image exist, which is exactly the set skimage keeps after cropping ``(win_size-1)//2`` pixels).  Used to pin
+    ``ssim`` above and the CUDA kernel against something that shares no code path with either."""
+    from numpy.lib.stride_tricks import sliding_window_view
+
+    x, y = original.astype(np.float64), predicted.astype(np.float64)
+    r = data_range(original, predicted)
+    wx = sliding_window_view(x, (win_size, win_size)).reshape(x.shape[0] - win_size + 1, x.shape[1] - win_size + 1, -1)
+    wy = sliding_window_view(y, (win_size, win_size)).reshape(wx.shape)
+    n = win_size * win_size
+    mx, my = wx.mean(axis=-1), wy.mean(axis=-1)
+    dx, dy = wx - mx[..., None], wy - my[..., None]
+    vx, vy, vxy = (dx * dx).sum(-1) / (n - 1), (dy * dy).sum(-1) / (n - 1), (dx * dy).sum(-1) / (n - 1)
+    c1, c2 = (k1 * r) ** 2, (k2 * r) ** 2
+    s = ((2 * mx * my + c1) * (2 * vxy + c2)) / ((mx * mx + my * my + c1) * (vx + vy + c2))
+    return float(s.mean())

@@ -17,6 +17,14 @@ MODEL_CASES = [
     ("nobias_w0_2", dict(seed=16, use_bias=False, w0=2.0, mod_bias_shift=0.5), "sine", dict(use_bias=False, w0=2.0)),
 ]
 
+# Weight scales at which an 11-bit significand no longer meets the 1e-3 bound (hidden W x 2, dense
+# modulations ~1): the cases the fp16x3 tensor-core mode exists for.  Same tuple layout as MODEL_CASES.
+HARD_CASES = [
+    ("sine_w2_dense", dict(seed=17, mod_bias_shift=1.0, hidden_weight_scale=2.0), "sine", {}),
+    ("morlet_w2_dense", dict(seed=18, mod_bias_shift=1.0, hidden_weight_scale=2.0), "morlet", {}),
+    ("sine_w3_dense", dict(seed=19, mod_bias_shift=1.0, hidden_weight_scale=3.0), "sine", {}),
+]
+
 
 def synth_tiles(seed: int, n: int, outer: int = 32) -> np.ndarray:
     """Smooth-ish non-negative patches in [0,1] (like normalised MRI magnitudes), with patch 1 black."""

@@ -158,3 +158,36 @@ def test_import_overlay_redirects_reference_imports():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_fma_pipe_gaussian_coefficients():
+    """csrc/tc_ptx.cuh gauss2: exp(-x^2/2) = 2^y by magic-number rounding + a degree-4 polynomial of the fraction +
+    an integer add into the exponent.  Emulated here in numpy fp32 (FMAs as fp64 products rounded once), with the
+    coefficient bit patterns parsed from the CUDA source: relative error <= 1e-5 where the envelope matters."""
+    import re
+    import struct
+
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mri_inr_b200", "csrc",
+                            "tc_ptx.cuh")).read()
+    body = src[src.index("uint64_t gauss2("):]
+    body = body[:body.index("return pk2(g0, g1);")]
+    lits = [int(x, 16) & 0xffffffff for x in re.findall(r"0x([0-9A-F]{16})ULL", body)]
+    f = [struct.unpack("<f", struct.pack("<I", v))[0] for v in lits]
+    negc, magic, magic2, c4, c3, c2, c1, c0 = f
+    assert magic == magic2 == 12582912.0 and abs(negc + 0.5 / np.log(2)) < 1e-7
+    x = np.concatenate([np.linspace(-14, 14, 400001), np.random.RandomState(0).normal(size=200000) * 2]).astype(np.float32)
+    t = np.minimum((x * x).astype(np.float32), np.float32(174.0))
+    y = t.astype(np.float64) * np.float64(np.float32(negc))
+    z = (y + magic).astype(np.float32)
+    nneg = (np.float32(magic) - z).astype(np.float32)
+    fr = (y + nneg.astype(np.float64)).astype(np.float32)
+    assert fr.min() >= -0.5001 and fr.max() <= 0.5001
+    p = np.full_like(fr, np.float32(c4))
+    for c in (c3, c2, c1, c0):
+        p = (p.astype(np.float64) * fr.astype(np.float64) + np.float64(np.float32(c))).astype(np.float32)
+    g = (p.view(np.int32) + (z.view(np.int32) << 23)).view(np.float32)
+    ref = np.exp(-0.5 * x.astype(np.float64) ** 2)
+    assert np.abs(g - ref).max() <= 5e-6
+    near = np.abs(x) < 9
+    assert np.abs(g[near] / ref[near] - 1).max() <= 1e-5
+    assert np.all(np.isfinite(g)) and np.all(g >= 0) and g[np.abs(x) > 13.5].max() < 1e-37

@@ -34,3 +34,32 @@ def test_metrics_restatement_properties():
     r = metrics.data_range(a, b)
     assert abs(metrics.psnr(a, b) - 10 * np.log10(r * r / np.mean((a.astype(np.float64) - b) ** 2))) < 1e-9
     assert metrics.psnr(a, b) > metrics.psnr(a, (a + 0.2).astype(np.float32))
+
+
+def test_ssim_two_independent_formulations_and_closed_forms():
+    """oracle/metrics.py is unpinned against scikit-image itself (absent here); what CAN be pinned: the filter-based
+    restatement against a direct per-window evaluation that shares no code with it, and closed forms."""
+    import numpy as np
+
+    from oracle import metrics
+
+    rs = np.random.RandomState(3)
+    for shape in ((64, 80), (33, 100), (7, 9)):
+        a = rs.uniform(0, 1, size=shape).astype(np.float32)
+        b = (a + 0.1 * rs.normal(size=shape)).astype(np.float32)
+        assert abs(metrics.ssim(a, b) - metrics.ssim_direct(a, b)) < 1e-12
+        assert abs(metrics.ssim_direct(a, a) - 1.0) < 1e-15
+    # y = x + c: contrast/structure terms cancel exactly, SSIM = mean over windows of the luminance term
+    x = rs.uniform(0.2, 0.8, size=(40, 40))
+    c = 0.1
+    y = x + c
+    from numpy.lib.stride_tricks import sliding_window_view
+
+    mx = sliding_window_view(x, (7, 7)).mean(axis=(-1, -2))
+    r = max(x.max(), y.max()) - min(x.min(), y.min())
+    c1 = (0.01 * r) ** 2
+    want = ((2 * mx * (mx + c) + c1) / (mx ** 2 + (mx + c) ** 2 + c1)).mean()
+    assert abs(metrics.ssim(x, y) - want) < 1e-12
+    # PSNR / NRMSE closed forms: y = x + c  =>  mse = c^2
+    assert abs(metrics.psnr(x, y) - 10 * np.log10(r ** 2 / c ** 2)) < 1e-9
+    assert abs(metrics.nrmse(x, y) - c / np.sqrt(np.mean(x ** 2))) < 1e-12

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import siren, tiling
-from oracle.synth import MODEL_CASES, synth_image, synth_tiles
+from oracle.synth import HARD_CASES, MODEL_CASES, synth_image, synth_tiles
 
 
 @pytest.mark.parametrize("s", [8, 16, 24, 32, 48])
@@ -29,7 +29,7 @@ def test_weight_matrix_bit_exact(golden, k):
     assert w.max() == 1.0
 
 
-@pytest.mark.parametrize("case", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
+@pytest.mark.parametrize("case", MODEL_CASES + HARD_CASES, ids=[c[0] for c in MODEL_CASES + HARD_CASES])
 def test_model_forward_matches_reference(golden, case):
     name, sd_kw, act, model_kw = case
     sd = siren.synth_state_dict(**sd_kw)
@@ -43,6 +43,13 @@ def test_model_forward_matches_reference(golden, case):
     # same ATen ops in the same order as the reference: agreement to fp32 rounding noise
     np.testing.assert_allclose(out.numpy(), g[f"{name}_out"], rtol=0, atol=2e-5)
     assert out.shape == (5, 24, 24)
+
+
+def test_hard_cases_span_the_output_range(golden):
+    """W x 2 / W x 3 with dense modulations: the regime where operand rounding shows."""
+    g = golden["model_forward"]
+    for name, *_ in HARD_CASES:
+        assert np.ptp(g[f"{name}_out"]) > 1.9
 
 
 def test_trained_like_case_is_sensitive(golden):

@@ -190,6 +190,26 @@ MRINR_API int64_t mrinr_image_metrics_scratch_bytes(int64_t N);
 MRINR_API int mrinr_image_metrics(const float* d_original, const float* d_predicted, int64_t N, int32_t H, int32_t W,
                         double* d_out, void* d_scratch, int64_t scratch_bytes, void* stream);
 
+/* ---- training: forward in train() mode (dropout after every hidden activation, modulated_siren.py:124,154-156) and
+ * the backward pass of the whole module, as Trainer._train_iteration needs them (src/train/training.py:177-207).
+ * mrinr_train_forward: d_tiles [B,32,32] -> d_out [B,C]; the intermediates stay in d_workspace
+ *   (mrinr_train_workspace_bytes(p, B) bytes, 256-byte aligned) for mrinr_train_backward, which must be given the same
+ *   weights view, tiles, dropout_p, seed and mask.  `p` are the packed weights of the CURRENT parameter values;
+ *   `weights` the fp32 parameters themselves.  Dropout: element kept iff hash(seed, layer, index) >= dropout_p * 2^32,
+ *   kept values scaled by 1/(1-p); d_keep_mask (optional, uint8 [L][B*C][H], 1 = keep) replaces the hash.
+ * mrinr_train_backward: d_dout [B,C] = d(loss)/d(out).  `grads` reuses the MrinrWeightsView layout: every non-null
+ *   pointer is a ZERO-INITIALISED, writable fp32 buffer of the parameter's shape that receives d(loss)/d(parameter)
+ *   (accumulated with atomics); the scalar fields and d_grid are ignored.
+ * Requires dim_hidden 256, latent_dim in {64,128,256}, an encoder in `p`.  fp32-class arithmetic throughout. */
+MRINR_API int64_t mrinr_train_workspace_bytes(const MrinrPacked* p, int64_t B);
+MRINR_API int mrinr_train_forward(const MrinrPacked* p, const MrinrWeightsView* weights, const float* d_tiles, int64_t B,
+                                  float dropout_p, uint64_t seed, const uint8_t* d_keep_mask, float* d_out,
+                                  void* d_workspace, int64_t workspace_bytes, void* stream);
+MRINR_API int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView* weights, const float* d_tiles,
+                                   const float* d_dout, int64_t B, float dropout_p, uint64_t seed,
+                                   const uint8_t* d_keep_mask, const MrinrWeightsView* grads, void* d_workspace,
+                                   int64_t workspace_bytes, void* stream);
+
 /* ---- peer memory for the one exchange step (gather of reconstructed slices to one rank) ---- */
 /* The reference has no distributed code; the multi-GPU sweep gathers every rank's reconstructed slices on one rank.
  * Instead of a collective after the reassembly, the gathering rank exports its [n_total,H,W] buffer and every other

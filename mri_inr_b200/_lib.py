@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "mrinr_image_metrics_scratch_bytes", "mrinr_image_metrics",
     "mrinr_fft2c_workspace_bytes", "mrinr_fft2c", "mrinr_kspace_to_image",
     "mrinr_peer_alloc", "mrinr_peer_open", "mrinr_peer_close", "mrinr_peer_free",
+    "mrinr_train_workspace_bytes", "mrinr_train_forward", "mrinr_train_backward",
 )
 
 
@@ -114,6 +115,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrinr_peer_close.argtypes = [c_void_p]
     lib.mrinr_peer_free.restype = c_int
     lib.mrinr_peer_free.argtypes = [c_void_p]
+    lib.mrinr_train_workspace_bytes.restype = c_int64
+    lib.mrinr_train_workspace_bytes.argtypes = [c_void_p, c_int64]
+    lib.mrinr_train_forward.restype = c_int
+    lib.mrinr_train_forward.argtypes = [c_void_p, POINTER(WeightsView), c_void_p, c_int64, c_float, ctypes.c_uint64,
+                                        c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.mrinr_train_backward.restype = c_int
+    lib.mrinr_train_backward.argtypes = [c_void_p, POINTER(WeightsView), c_void_p, c_void_p, c_int64, c_float,
+                                         ctypes.c_uint64, c_void_p, POINTER(WeightsView), c_void_p, c_int64, c_void_p]
 
 
 def load() -> ctypes.CDLL:

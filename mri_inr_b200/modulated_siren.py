@@ -3,14 +3,19 @@
 Same 17 constructor keyword arguments (modulated_siren.py:349-367, call site test_mod_siren.py:96-114),
 same ``state_dict`` layout (31 tensors: ``grid``, ``net.layers.{i}.{weight,bias}``, ``net.last_layer.*``,
 ``modulator.layers.{i}.0.*``, ``encoder.encoder.encoder.{0,2,4,7}.*``) and the same
-``forward(tiles [B,32,32]) -> [B,S,S]`` (modulated_siren.py:435-457) -- but the forward is inference only
-and runs on the hand-written sm_100a kernels of ``libmrinr.so``:
+``forward(tiles [B,32,32]) -> [B,S,S]`` (modulated_siren.py:435-457), running on the hand-written sm_100a
+kernels of ``libmrinr.so``.  Under ``eval()`` + ``torch.no_grad()`` (test_mod_siren.py:131-132,193-194):
 
 * patch encoder: two fused strided convolutions (fp32 FFMA) + the 8x8 convolution and the linear layer as
   split-fp16 tcgen05 products (``mrinr_encoder_forward``),
 * modulator: one split-fp16 tcgen05 launch per layer (``mrinr_modulator_forward``; fp32 FFMA in "fp32" mode),
 * synthesis net over the coordinate grid of every patch: one persistent tcgen05 kernel
   (``mrinr_siren_forward``); the coordinates are the module's ``grid`` buffer, as in the reference (:448).
+
+In ``train()`` mode or with gradients enabled (``Trainer._train_iteration``, src/train/training.py:177-207) the
+forward applies dropout after every hidden activation (modulated_siren.py:124,154-156) and is differentiable with
+respect to every parameter -- ``mrinr_train_forward`` / ``mrinr_train_backward`` (csrc/train.cu) behind a
+``torch.autograd.Function``.
 
 There is no CPU path and no library (cuDNN / cuBLAS) route: CPU tensors and unsupported shapes raise.
 """
@@ -46,6 +51,40 @@ def make_grid_host(siren_patch_size: int) -> torch.Tensor:
                 lin[i] = np.float32(1.0 - np.float64(step) * (s - 1 - i))
     c = np.arange(s * s)
     return torch.from_numpy(np.stack([lin[c // s], lin[c % s]], axis=1).astype(np.float32))
+
+
+class _TrainFunction(torch.autograd.Function):
+    """``ModulatedSiren.forward`` in training mode as one differentiable op: the forward and the backward are each a
+    sequence of launches of csrc/train.cu through the C ABI.  ``params`` is ``model._train_params()`` (passed so that
+    autograd tracks them); their gradients come back in the same order."""
+
+    @staticmethod
+    def forward(ctx, model, tiles, seed, keep_mask, *params):
+        packed = model._packed()
+        view, keep = model._weights_view()
+        B = tiles.shape[0]
+        ws = torch.empty(ops.train_workspace_bytes(packed, B), dtype=torch.uint8, device=tiles.device)
+        out = ops.train_forward(packed, view, tiles, model.dropout if model.training else 0.0, seed, keep_mask, ws)
+        ctx.model, ctx.tiles, ctx.ws, ctx.seed, ctx.keep_mask = model, tiles, ws, seed, keep_mask
+        ctx.p = model.dropout if model.training else 0.0
+        ctx.view, ctx.keep, ctx.packed = view, keep, packed
+        ctx.needs = [p is not None and p.requires_grad for p in params]
+        s = model.siren_patch_size
+        return out.view(B, s, s)
+
+    @staticmethod
+    def backward(ctx, dout):
+        model = ctx.model
+        params = model._train_params()
+        # every existing parameter gets a zero-initialised fp32 buffer (the kernels accumulate with atomics)
+        grads = [None if p is None else torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in params]
+        gview, gkeep = model._weights_view(tensors=grads)
+        ops.train_backward(ctx.packed, ctx.view, gview, ctx.tiles,
+                           dout.contiguous().view(ctx.tiles.shape[0], -1).to(torch.float32), ctx.p, ctx.seed,
+                           ctx.keep_mask, ctx.ws)
+        del gkeep
+        ctx.ws = None
+        return (None, None, None, None) + tuple(g if need else None for g, need in zip(grads, ctx.needs))
 
 
 class Siren(nn.Module):
@@ -291,12 +330,47 @@ class ModulatedSiren(nn.Module):
         return self._pack
 
     def _check_inference(self) -> None:
+        """The batched pipeline and the two halves ``modulations`` / ``synthesize`` are inference-only entry points
+        (no dropout, no autograd graph); ``forward`` itself also serves training."""
         if self.training and self.dropout > 0:
-            raise RuntimeError("mri_inr_b200.ModulatedSiren is inference only: call .eval() "
-                               "(the reference applies dropout in training mode, modulated_siren.py:124,156)")
+            raise RuntimeError("this entry point is inference only: call .eval() (in train() mode the reference applies "
+                               "dropout, modulated_siren.py:124,156; use forward(tiles) for training)")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("mri_inr_b200.ModulatedSiren has no backward: call it under torch.no_grad() as "
-                               "test_mod_siren.py:131-132 does")
+            raise RuntimeError("this entry point builds no autograd graph: call it under torch.no_grad() as "
+                               "test_mod_siren.py:131-132 does (use forward(tiles) for training)")
+
+    # ---- training (src/train/training.py:177-207)
+    def _train_params(self):
+        """Every parameter in the order of the C ABI's weights view (``None`` where ``use_bias=False``)."""
+        ts = []
+        for layer in self.net.layers:
+            ts += [layer.weight, layer.bias]
+        ts += [self.net.last_layer.weight, self.net.last_layer.bias]
+        for seq in self.modulator.layers:
+            ts += [seq[0].weight, seq[0].bias]
+        ts += self.encoder.params()
+        return ts
+
+    def _weights_view(self, tensors=None):
+        """``MrinrWeightsView`` over the parameters -- or over ``tensors``, a list shaped like ``_train_params()``
+        (the gradient buffers; ``None`` only where the parameter itself does not exist)."""
+        ts = self._train_params() if tensors is None else list(tensors)
+        L = self.num_layers
+        mod = ts[2 * L + 2: 4 * L + 2]
+        return ops.weights_view(grid=self.grid, net_weights=ts[0:2 * L:2], net_biases=ts[1:2 * L:2],
+                                last_weight=ts[2 * L], last_bias=ts[2 * L + 1], mod_weights=mod[0::2],
+                                mod_biases=mod[1::2], w0=self.net.w0, w0_initial=self.net.w0_initial,
+                                activation=self.activation, siren_patch_size=self.siren_patch_size,
+                                encoder_params=ts[4 * L + 2:], outer_patch_size=self.outer_patch_size,
+                                allow_none=tensors is not None)
+
+    def _forward_train(self, tiles: torch.Tensor) -> torch.Tensor:
+        if self.dim_hidden != 256:
+            raise RuntimeError("the training path needs dim_hidden == 256")
+        # dropout seed from torch's generator: reproducible under torch.manual_seed, different every call
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        mask = getattr(self, "_train_keep_mask", None)       # test hook: an explicit uint8 keep-mask [L, B*C, H]
+        return _TrainFunction.apply(self, tiles, seed, mask, *self._train_params())
 
     # ---- the two halves of forward, exposed for the batched pipeline
     def modulations(self, tiles: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -315,10 +389,12 @@ class ModulatedSiren(nn.Module):
         return y.view(-1, s, s)
 
     def forward(self, tiles: torch.Tensor) -> torch.Tensor:
-        self._check_inference()
         if not tiles.is_cuda:
             raise RuntimeError("tiles must be a CUDA tensor: mri_inr_b200 has no CPU path")
         if tiles.shape[0] == 0:
             return tiles.new_zeros((0, self.siren_patch_size, self.siren_patch_size))
         tiles = tiles.to(torch.float32).contiguous()
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad or (self.training and self.dropout > 0):
+            return self._forward_train(tiles)
         return self.synthesize(self.modulations(tiles))

@@ -27,6 +27,78 @@ def make_grid(siren_patch_size: int, device) -> torch.Tensor:
     return out
 
 
+def weights_view(*, grid: torch.Tensor, net_weights: Sequence[torch.Tensor],
+                 net_biases: Sequence[Optional[torch.Tensor]], last_weight: torch.Tensor,
+                 last_bias: Optional[torch.Tensor], mod_weights: Sequence[torch.Tensor],
+                 mod_biases: Sequence[torch.Tensor], w0: float, w0_initial: float, activation: str,
+                 siren_patch_size: int, encoder_params: Optional[Sequence[torch.Tensor]] = None,
+                 outer_patch_size: int = 32, allow_none: bool = False):
+    """A ``MrinrWeightsView`` (include/mrinr.h) over fp32 CUDA tensors: ``(view, keepalive)``.  The keepalive list owns
+    the ctypes pointer arrays and any converted copies: it must outlive every use of ``view``.  The same struct carries
+    gradient buffers for ``mrinr_train_backward`` (``allow_none``: missing tensors become null pointers)."""
+    if activation not in _lib.ACTIVATIONS:
+        # the reference treats anything but "morlet" as sine (modulated_siren.py:120-123)
+        activation = "sine"
+    L = len(net_weights)
+    dev = grid.device
+    keep = []
+
+    def f32(t, name):
+        t = _lib.require_cuda(t.detach(), name)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            if allow_none:
+                raise RuntimeError(f"{name} must be a contiguous fp32 tensor")
+            t = t.to(torch.float32).contiguous()
+        if t.device != dev:
+            raise RuntimeError(f"{name} is on {t.device}, expected {dev}")
+        keep.append(t)
+        return t
+
+    def ptr_array(ts, name):
+        arr = (c_void_p * L)()
+        for i, t in enumerate(ts):
+            arr[i] = None if t is None else f32(t, f"{name}[{i}]").data_ptr()
+        keep.append(arr)
+        return arr
+
+    H = net_weights[0].shape[0]
+    view = _lib.WeightsView()
+    view.dim_in = net_weights[0].shape[1]
+    view.dim_hidden = H
+    view.dim_out = last_weight.shape[0]
+    view.num_layers = L
+    view.latent_dim = mod_weights[0].shape[1]
+    view.siren_patch_size = siren_patch_size
+    view.w0 = float(w0)
+    view.w0_initial = float(w0_initial)
+    view.activation = _lib.ACTIVATIONS[activation]
+    view.d_grid = f32(grid, "grid").data_ptr()
+    if tuple(grid.shape) != (siren_patch_size * siren_patch_size, 2):
+        raise RuntimeError(f"grid has shape {tuple(grid.shape)}, expected {(siren_patch_size ** 2, 2)}")
+    view.d_net_weight = ctypes.cast(ptr_array(net_weights, "net.layers.weight"), ctypes.POINTER(c_void_p))
+    view.d_net_bias = ctypes.cast(ptr_array(net_biases, "net.layers.bias"), ctypes.POINTER(c_void_p))
+    view.d_mod_weight = ctypes.cast(ptr_array(mod_weights, "modulator.layers.weight"), ctypes.POINTER(c_void_p))
+    view.d_mod_bias = ctypes.cast(ptr_array(mod_biases, "modulator.layers.bias"), ctypes.POINTER(c_void_p))
+    view.d_last_weight = f32(last_weight, "net.last_layer.weight").data_ptr()
+    view.d_last_bias = None if last_bias is None else f32(last_bias, "net.last_layer.bias").data_ptr()
+    # patch encoder (optional): conv1 w,b, conv2 w,b, conv3 w,b, fc w,b  (siren_encoder.py:503-512)
+    view.outer_patch_size = int(outer_patch_size)
+    if encoder_params is not None:
+        names = ("conv1_weight", "conv1_bias", "conv2_weight", "conv2_bias", "conv3_weight", "conv3_bias",
+                 "fc_weight", "fc_bias")
+        shapes = ((16, 1, 3, 3), (16,), (32, 16, 3, 3), (32,), (64, 32, 8, 8), (64,), (view.latent_dim, 64),
+                  (view.latent_dim,))
+        if len(encoder_params) != 8:
+            raise RuntimeError("encoder_params must hold 8 tensors (3 convolutions + 1 linear, weight and bias)")
+        for n, shp, t in zip(names, shapes, encoder_params):
+            if t is None and allow_none:
+                continue
+            if tuple(t.shape) != shp:
+                raise RuntimeError(f"encoder {n} has shape {tuple(t.shape)}, expected {shp}")
+            setattr(view, "d_enc_" + n, f32(t, "encoder." + n).data_ptr())
+    return view, keep
+
+
 class PackedWeights:
     """Owner of a ``MrinrPacked`` handle (re-tiled weights, layer-0 table)."""
 
@@ -38,67 +110,17 @@ class PackedWeights:
                  encoder_params: Optional[Sequence[torch.Tensor]] = None, outer_patch_size: int = 32):
         lib = _lib.load()
         if activation not in _lib.ACTIVATIONS:
-            # the reference treats anything but "morlet" as sine (modulated_siren.py:120-123)
             activation = "sine"
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
         L = len(net_weights)
         dev = grid.device
-        keep = []
-
-        def f32(t, name):
-            t = _lib.require_cuda(t.detach(), name)
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                t = t.to(torch.float32).contiguous()
-            if t.device != dev:
-                raise RuntimeError(f"{name} is on {t.device}, expected {dev}")
-            keep.append(t)
-            return t
-
-        def ptr_array(ts, name):
-            arr = (c_void_p * L)()
-            for i, t in enumerate(ts):
-                arr[i] = None if t is None else f32(t, f"{name}[{i}]").data_ptr()
-            return arr
-
         H = net_weights[0].shape[0]
-        view = _lib.WeightsView()
-        view.dim_in = net_weights[0].shape[1]
-        view.dim_hidden = H
-        view.dim_out = last_weight.shape[0]
-        view.num_layers = L
-        view.latent_dim = mod_weights[0].shape[1]
-        view.siren_patch_size = siren_patch_size
-        view.w0 = float(w0)
-        view.w0_initial = float(w0_initial)
-        view.activation = _lib.ACTIVATIONS[activation]
-        view.d_grid = f32(grid, "grid").data_ptr()
-        if tuple(grid.shape) != (siren_patch_size * siren_patch_size, 2):
-            raise RuntimeError(f"grid has shape {tuple(grid.shape)}, expected {(siren_patch_size ** 2, 2)}")
-        nw = ptr_array(net_weights, "net.layers.weight")
-        nb = ptr_array(net_biases, "net.layers.bias")
-        mw = ptr_array(mod_weights, "modulator.layers.weight")
-        mb = ptr_array(mod_biases, "modulator.layers.bias")
-        view.d_net_weight = ctypes.cast(nw, ctypes.POINTER(c_void_p))
-        view.d_net_bias = ctypes.cast(nb, ctypes.POINTER(c_void_p))
-        view.d_mod_weight = ctypes.cast(mw, ctypes.POINTER(c_void_p))
-        view.d_mod_bias = ctypes.cast(mb, ctypes.POINTER(c_void_p))
-        view.d_last_weight = f32(last_weight, "net.last_layer.weight").data_ptr()
-        view.d_last_bias = None if last_bias is None else f32(last_bias, "net.last_layer.bias").data_ptr()
-        # patch encoder (optional): conv1 w,b, conv2 w,b, conv3 w,b, fc w,b  (siren_encoder.py:503-512)
-        view.outer_patch_size = int(outer_patch_size)
+        view, keep = weights_view(grid=grid, net_weights=net_weights, net_biases=net_biases, last_weight=last_weight,
+                                  last_bias=last_bias, mod_weights=mod_weights, mod_biases=mod_biases, w0=w0,
+                                  w0_initial=w0_initial, activation=activation, siren_patch_size=siren_patch_size,
+                                  encoder_params=encoder_params, outer_patch_size=outer_patch_size)
         self.has_encoder = encoder_params is not None
-        if encoder_params is not None:
-            names = ("conv1_weight", "conv1_bias", "conv2_weight", "conv2_bias", "conv3_weight", "conv3_bias",
-                     "fc_weight", "fc_bias")
-            shapes = ((16, 1, 3, 3), (16,), (32, 16, 3, 3), (32,), (64, 32, 8, 8), (64,), (view.latent_dim, 64),
-                      (view.latent_dim,))
-            if len(encoder_params) != 8:
-                raise RuntimeError("encoder_params must hold 8 tensors (3 convolutions + 1 linear, weight and bias)")
-            for n, shp, t in zip(names, shapes, encoder_params):
-                if tuple(t.shape) != shp:
-                    raise RuntimeError(f"encoder {n} has shape {tuple(t.shape)}, expected {shp}")
-                setattr(view, "d_enc_" + n, f32(t, "encoder." + n).data_ptr())
         handle = c_void_p()
         with torch.cuda.device(dev):
             rc = lib.mrinr_pack_weights(ctypes.byref(view), _lib.PRECISIONS[precision], _lib.stream_ptr(dev),
@@ -373,3 +395,43 @@ def kspace_to_image(kspace: torch.Tensor, column_mask: Optional[torch.Tensor] = 
         _lib.check(lib.mrinr_kspace_to_image(k.data_ptr(), _ptr(mask), N, H, W, out.data_ptr(), ws.data_ptr(),
                                              ws.numel() * 4, _lib.stream_ptr(k.device)), "kspace_to_image")
     return out[0] if squeeze else out
+
+
+def train_workspace_bytes(packed: PackedWeights, B: int) -> int:
+    return int(_lib.load().mrinr_train_workspace_bytes(packed.handle, B))
+
+
+def train_forward(packed: PackedWeights, view, tiles: torch.Tensor, dropout_p: float, seed: int,
+                  keep_mask: Optional[torch.Tensor], workspace: torch.Tensor) -> torch.Tensor:
+    """``ModulatedSiren.forward`` in ``train()`` mode (dropout after every hidden activation,
+    modulated_siren.py:124,154-156): tiles ``[B,32,32]`` -> ``[B, S*S]``; the intermediates stay in ``workspace``
+    (``train_workspace_bytes(packed, B)`` bytes) for :func:`train_backward`."""
+    lib = _lib.load()
+    _lib.require_cuda(tiles, "tiles", torch.float32)
+    B = tiles.shape[0]
+    out = torch.empty(B, packed.C, dtype=torch.float32, device=tiles.device)
+    if keep_mask is not None:
+        _lib.require_cuda(keep_mask, "keep_mask", torch.uint8)
+        if keep_mask.numel() != packed.L * B * packed.C * packed.H:
+            raise RuntimeError(f"keep_mask must have L*B*C*H = {packed.L * B * packed.C * packed.H} entries")
+    with torch.cuda.device(tiles.device):
+        _lib.check(lib.mrinr_train_forward(packed.handle, ctypes.byref(view), tiles.data_ptr(), B, float(dropout_p),
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(keep_mask), out.data_ptr(),
+                                           workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                           _lib.stream_ptr(tiles.device)), "train_forward")
+    return out
+
+
+def train_backward(packed: PackedWeights, view, grads_view, tiles: torch.Tensor, dout: torch.Tensor, dropout_p: float,
+                   seed: int, keep_mask: Optional[torch.Tensor], workspace: torch.Tensor) -> None:
+    """Backward of :func:`train_forward`: ``dout [B, S*S]`` -> gradients accumulated into the zero-initialised
+    buffers of ``grads_view`` (a ``weights_view`` over gradient tensors)."""
+    lib = _lib.load()
+    _lib.require_cuda(dout, "dout", torch.float32)
+    B = tiles.shape[0]
+    with torch.cuda.device(tiles.device):
+        _lib.check(lib.mrinr_train_backward(packed.handle, ctypes.byref(view), tiles.data_ptr(), dout.data_ptr(), B,
+                                            float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(keep_mask),
+                                            ctypes.byref(grads_view), workspace.data_ptr(),
+                                            workspace.numel() * workspace.element_size(),
+                                            _lib.stream_ptr(tiles.device)), "train_backward")

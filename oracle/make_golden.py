@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from . import ref_import, siren
-from .synth import HARD_CASES, MODEL_CASES, synth_image, synth_tiles
+from .synth import (GRAD_SAMPLE, HARD_CASES, MODEL_CASES, TRAIN_BATCH, TRAIN_CASES, grad_sample_index, synth_image,
+                    synth_tiles, train_keep_mask)
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -54,6 +55,46 @@ def main() -> None:
         out[f"{name}_mods"] = torch.stack(list(mods)).numpy()
         out[f"{name}_out"] = y.numpy()
     np.savez_compressed(os.path.join(GOLDEN_DIR, "model_forward.npz"), **out)
+
+    # ---- training iteration (src/train/training.py:177-207): the reference module in train() mode, MSE against the
+    # centre crop of the fully sampled patches (extract_center_batch, tiling.py:306-322), autograd for every parameter.
+    # Dropout: nn.Dropout(p) of every hidden layer (modulated_siren.py:124) is swapped for a module that applies a
+    # FIXED keep-mask with the same 1/(1-p) scaling, so that both sides see the same mask.
+    class FixedDropout(torch.nn.Module):
+        def __init__(self, keep, p):
+            super().__init__()
+            self.keep, self.p = keep, p
+
+        def forward(self, x):
+            return x * self.keep.view_as(x) / (1.0 - self.p)
+
+    out = {}
+    for name, sd_kw, act, p in TRAIN_CASES:
+        sd = siren.synth_state_dict(**sd_kw)
+        model = ref_import.build_reference_model(activation=act)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        B, S, H, L = TRAIN_BATCH, 24, 256, 5
+        if p > 0:
+            keep = torch.from_numpy(train_keep_mask(1000 + sd_kw["seed"], L, B * S * S, H, p)).float()
+            for l, layer in enumerate(model.net.layers):
+                layer.dropout = FixedDropout(keep[l], p)
+        else:
+            for layer in model.net.layers:
+                layer.dropout = torch.nn.Identity()
+        under = torch.from_numpy(synth_tiles(300 + sd_kw["seed"], B))
+        full = torch.from_numpy(synth_tiles(400 + sd_kw["seed"], B))
+        target = ref.tiling.extract_center_batch(full, 32, 24).float()          # training.py:190-196
+        outputs = model(under)                                                   # :199
+        loss = torch.nn.functional.mse_loss(outputs, target)                     # criterion "MSE", :108-114, :200
+        loss.backward()                                                          # :201 (no GradScaler on the CPU)
+        out[f"{name}_out"] = outputs.detach().numpy()
+        out[f"{name}_loss"] = np.array(loss.item(), dtype=np.float64)
+        for k, prm in model.named_parameters():
+            g = prm.grad.detach().numpy().reshape(-1)
+            out[f"{name}_gnorm_{k}"] = np.array(np.sqrt((g.astype(np.float64) ** 2).sum()))
+            out[f"{name}_gsample_{k}"] = g[grad_sample_index(g.size)].copy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "training.npz"), **out)
 
     # ---- tiling (src/util/tiling.py) on odd-sized and baseline-sized images
     out = {}

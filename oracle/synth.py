@@ -44,3 +44,27 @@ def synth_image(seed: int, h: int, w: int) -> np.ndarray:
     return img
 
 
+
+
+# Training parity cases (src/train/training.py:177-207): (name, synth_state_dict kwargs, activation, dropout p).
+# p = 0: dropout off; p > 0: a FIXED keep-mask (train_keep_mask) replaces torch's dropout RNG on both sides.
+TRAIN_CASES = [
+    ("train_sine_nodrop", dict(seed=12, mod_bias_shift=0.5), "sine", 0.0),
+    ("train_sine_drop", dict(seed=12, mod_bias_shift=0.5), "sine", 0.1),
+    ("train_morlet_drop", dict(seed=14, mod_bias_shift=0.5), "morlet", 0.1),
+]
+TRAIN_BATCH = 3
+GRAD_SAMPLE = 2048
+
+
+def train_keep_mask(seed: int, num_layers: int, rows: int, hidden: int, p: float) -> np.ndarray:
+    """uint8 keep-mask ``[L, rows, H]`` (1 = keep, probability 1 - p), rows = B * S * S."""
+    rs = np.random.RandomState(seed)
+    return (rs.random_sample((num_layers, rows, hidden)) >= p).astype(np.uint8)
+
+
+def grad_sample_index(numel: int) -> np.ndarray:
+    """Fixed sample of a flattened gradient (all of it when small): what the golden files keep per parameter."""
+    if numel <= GRAD_SAMPLE:
+        return np.arange(numel)
+    return (np.arange(GRAD_SAMPLE, dtype=np.int64) * numel) // GRAD_SAMPLE

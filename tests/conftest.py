@@ -33,4 +33,4 @@ def golden():
     import numpy as np
 
     return {name: np.load(os.path.join(GOLDEN, name + ".npz"))
-            for name in ("grid_weights", "model_forward", "tiling", "normalize")}
+            for name in ("grid_weights", "model_forward", "tiling", "normalize", "training")}

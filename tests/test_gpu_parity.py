@@ -509,13 +509,17 @@ def test_metrics_error_mirror_matches_reference_flow():
     assert abs(got[0] - want[0]) <= 0.05 and abs(got[1] - want[1]) <= 1e-3 and abs(got[2] - want[2]) <= 1e-3
 
 
-def test_cpu_tensors_and_grad_are_refused():
+def test_cpu_tensors_are_refused_and_grad_mode_is_differentiable():
+    from mri_inr_b200.pipeline import ReconstructionPipeline
+
     name, sd_kw, act, model_kw = MODEL_CASES[0]
     m, sd = _model(sd_kw, act, model_kw, "fp16")
     with torch.no_grad(), pytest.raises(RuntimeError):
         m(torch.zeros(2, 32, 32))
-    with pytest.raises(RuntimeError):
-        m(torch.zeros(2, 32, 32, device=DEV))          # grad enabled
+    y = m(torch.rand(2, 32, 32, device=DEV))           # grad enabled: the training path (csrc/train.cu), eval = no dropout
+    assert y.requires_grad and y.shape == (2, 24, 24)
+    with pytest.raises(RuntimeError):                  # the batched pipeline stays inference-only
+        ReconstructionPipeline(m).reconstruct(torch.rand(1, 320, 320, device=DEV))
 
 
 def test_full_size_properties():

@@ -86,8 +86,14 @@ def test_no_cpu_path_and_inference_only():
     with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(2, 32, 32))
     m.train()
-    with torch.no_grad(), pytest.raises(RuntimeError, match="eval"):
+    with pytest.raises(RuntimeError, match="CUDA"):          # the training path is CUDA-only as well
         m(torch.zeros(2, 32, 32))
+    # the batched pipeline and the two halves of forward are inference-only entry points
+    with torch.no_grad(), pytest.raises(RuntimeError, match="eval"):
+        m._check_inference()
+    m.eval()
+    with pytest.raises(RuntimeError, match="no_grad"):
+        m._check_inference()
     from mri_inr_b200 import ops
 
     with pytest.raises(RuntimeError, match="CUDA"):

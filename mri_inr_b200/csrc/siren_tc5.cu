@@ -339,6 +339,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
     // operand entries of columns cg*kCols + hc*16 .. +15 of row t: pk into slot's A buffer; X3: lo into the second one
     auto store16 = [&](int slot, int hc, const uint32_t (&pk)[8], const uint32_t (&lo)[8]) {
       uint8_t* base = smem + kOffA + slot * 65536 + (cg * (kCols / 8) + hc * 2) * 2048 + t * 16;
+#ifdef MRINR_POWER_NO_STS      // tools/power_split.py only: wrong results, the operand stores never execute (what an
+      if (P.w0 != 12345.f) {   // A operand that does not go through shared memory could save at most)
+        asm volatile("" ::"r"(pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7]));
+        return;
+      }
+#endif
       *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(base + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       if (X3) {
@@ -608,7 +614,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
                                            desc_hi, idesc, 1u);
                     }
                   } else if (pass == 0) {
+#ifndef MRINR_POWER_NO_BIAS    // tools/power_split.py only: what the 17th K step (bias through the MMA) costs
                     umma_f16_pair_lohi(d_tmem, ones_lo, b_lo, desc_hi, idesc, 1u);      // + bias
+#endif
                   }
 #endif
                   // The last slot is the last user of a slab: hand every slab back as soon as its MMAs are issued, so

@@ -1,8 +1,10 @@
 """Where does the power go?  Runs the synthesis kernel back to back for a few seconds and samples nvidia-smi
 (power draw, SM clock) meanwhile.  Use with instrumented builds (make -C mri_inr_b200/csrc power):
     python tools/power_split.py                                   # the product kernel
-    MRINR_LIB=build/libmrinr_nomma.so python tools/power_split.py # epilogue only (no tcgen05.mma issued)
-    MRINR_LIB=build/libmrinr_nosin.so python tools/power_split.py # MMAs + epilogue without MUFU.SIN
+    MRINR_LIB=build/libmrinr_NO_MMA.so python tools/power_split.py # epilogue only (no tcgen05.mma issued)
+    MRINR_LIB=build/libmrinr_NO_SIN.so python tools/power_split.py # MMAs + epilogue without MUFU.SIN
+    MRINR_LIB=build/libmrinr_NO_BIAS.so ...                        # without the 17th K step (bias through the MMA)
+    MRINR_LIB=build/libmrinr_NO_STS.so ...                         # without the operand stores to shared memory
 The instrumented builds compute wrong results; they exist for this measurement only."""
 import os, subprocess, sys, threading, time, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -238,19 +238,21 @@ class SharedHostBuffer:
         dist.all_reduce(flag)
         self.ok = int(flag.item()) == 0
         if not self.ok:
-            self.close()
+            self.close(barrier=False)              # the all_reduce above already lined the ranks up
 
-    def close(self):
+    def close(self, barrier=True):
+        """Collective (one barrier) unless ``barrier=False`` (the caller has just synchronised the ranks itself)."""
         import torch
         import torch.distributed as dist
 
+        if barrier:
+            dist.barrier()                          # nobody writes into the buffer any more
         if self.tensor is not None and self._registered:
             torch.cuda.synchronize()
             torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
             self._registered = False
         self.tensor = None
-        dist.barrier()                              # nobody maps the file any more
-        if self.rank == 0:
+        if self.rank == 0:                          # unlinking while other ranks still map the file is fine on POSIX
             try:
                 os.unlink(self.path)
             except OSError:
@@ -491,19 +493,26 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
-    # ---- teardown.  The measurement is complete and printed; every step below is collective and runs on every rank
-    # in the same order.  A failure here is reported on stderr but does not turn a finished measurement into rc != 0.
+    # ---- teardown.  The measurement is complete and printed.  ONE barrier (every rank is done with the shared host
+    # buffer and the peer-mapped device buffer), then only local clean-up: no collective runs after a mapping has been
+    # closed (see PeerGather._release).  A failure here is reported on stderr but does not turn a finished measurement
+    # into rc != 0 (SCALE_r01's N=4 point died in this region on exactly the two ring neighbours of rank 0).
     if world > 1:
         try:
             recon = None
-            if shared is not None:
-                shared.close()
-            if peer is not None:
-                peer.close()
+            torch.cuda.synchronize()
             dist.barrier()
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            if shared is not None:
+                shared.close(barrier=False)
+            if peer is not None:
+                peer.close(barrier=False)
         except Exception as e:  # noqa: BLE001
             print(f"[bench] rank {rank}: teardown: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
+        try:
+            dist.destroy_process_group()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: destroy_process_group: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
 
 
 def main():

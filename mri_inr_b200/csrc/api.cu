@@ -23,8 +23,21 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Error codes that a kernel launch can never produce but that other components of the process leave behind in the
+// runtime's (non-sticky) last-error slot: peer access enabled twice (this library's lazy CUDA-IPC mapping and NCCL's
+// P2P transport both enable it towards rank 0's GPU -- on exactly the ring neighbours of rank 0), host memory
+// registered twice.  They are not ours to report: a stale one would turn the next launch into a spurious failure.
+static bool benign_stale_error(cudaError_t e) {
+  return e == cudaErrorPeerAccessAlreadyEnabled || e == cudaErrorPeerAccessNotEnabled ||
+         e == cudaErrorHostMemoryAlreadyRegistered || e == cudaErrorHostMemoryNotRegistered;
+}
+
 int check_launch(const char* what) {
-  const cudaError_t e = cudaPeekAtLastError();
+  cudaError_t e = cudaPeekAtLastError();
+  if (benign_stale_error(e)) {
+    (void)cudaGetLastError();          // clear it, then look again
+    e = cudaPeekAtLastError();
+  }
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -384,6 +397,8 @@ extern "C" int mrinr_peer_open(const uint8_t* handle, void** d_ptr) {
   memcpy(&h, handle, sizeof(h));
   void* p = nullptr;
   MRINR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  // the lazy peer-access enable can leave cudaErrorPeerAccessAlreadyEnabled behind when NCCL got there first
+  if (benign_stale_error(cudaPeekAtLastError())) (void)cudaGetLastError();
   *d_ptr = p;
   return 0;
 }

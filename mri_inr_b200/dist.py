@@ -175,30 +175,31 @@ class PeerGather:
         dist.barrier(group=self.group)
         return self.full if self._owner else None
 
-    def _release(self) -> None:
-        """(1) non-owners unmap, (2) ONE barrier that every rank takes whatever its local state, (3) the owner
-        frees -- so nobody still maps the buffer when it is freed, and the collective sequence is the same on every
-        rank even after a partial failure."""
+    def _release(self, barrier: bool = True) -> None:
+        """ONE barrier that every rank takes whatever its local state (nobody stores into the buffer any more), then
+        the purely local part: non-owners unmap, the owner frees.  No collective runs AFTER a mapping has been closed:
+        the peer access that the lazy CUDA-IPC mapping shares with NCCL's P2P transport (towards the owner's GPU, on the
+        owner's ring neighbours) must not be torn down underneath a collective.  The collective sequence is the same
+        on every rank even after a partial failure."""
         errors = []
         self.full = self.local_view = None
         with self._device_ctx():
             self._sync()
-            if self._ptr and not self._owner:
-                if self.backend.close(self._ptr) != 0:
-                    errors.append("mrinr_peer_close: " + self.backend.last_error())
-                self._ptr = 0
-            if dist.is_initialized():
+            if barrier and dist.is_initialized():
                 dist.barrier(group=self.group)
-            if self._ptr and self._owner:
-                if self.backend.free(self._ptr) != 0:
-                    errors.append("mrinr_peer_free: " + self.backend.last_error())
+                self._sync()
+            if self._ptr:
+                rc = self.backend.free(self._ptr) if self._owner else self.backend.close(self._ptr)
+                if rc != 0:
+                    errors.append(("mrinr_peer_free: " if self._owner else "mrinr_peer_close: ") + self.backend.last_error())
                 self._ptr = 0
         if errors:
             raise RuntimeError("PeerGather release failed: " + "; ".join(errors))
 
-    def close(self) -> None:
-        """Collective: call it on every rank (idempotent only across ALL ranks together)."""
+    def close(self, barrier: bool = True) -> None:
+        """Collective (one barrier) unless ``barrier=False``: then the caller guarantees that every rank has finished
+        with the buffer (e.g. it has just run its own barrier) and the call is purely local."""
         if getattr(self, "_closed", False):
             return
         self._closed = True
-        self._release()
+        self._release(barrier)

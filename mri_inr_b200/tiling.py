@@ -1,8 +1,8 @@
 """Drop-in for the inference functions of the reference's ``src/util/tiling.py`` (same names, argument
 meaning and return values), running on the coalesced HBM kernels of ``libmrinr.so``.
 
-Out of scope (training only): ``filter_black_patches``, ``filter_black_patches_indices``,
-``extract_center_batch``.
+The three training-side helpers (``filter_black_patches``, ``filter_black_patches_indices``, ``extract_center_batch``;
+tiling.py:201-241,306-322) are mirrored too, so that ``src/train/training.py:18-25`` resolves under the import overlay.
 """
 from __future__ import annotations
 
@@ -84,3 +84,25 @@ def reintegrate_black_patches(processed_patches: torch.Tensor, black_indices, or
         keep[torch.as_tensor(list(black_indices), dtype=torch.long, device=processed_patches.device)] = False
     full[keep] = processed_patches
     return full
+
+
+def filter_black_patches_indices(undersampled: torch.Tensor) -> List[int]:
+    """tiling.py:227-241: indices of the non-black patches (one classifier launch instead of a loop of syncs)."""
+    mask = ops.classify_patches(undersampled.to(torch.float32).contiguous())
+    return (mask == 0).nonzero(as_tuple=True)[0].tolist()
+
+
+def filter_black_patches(undersampled: List[torch.Tensor], fullysampled: List[torch.Tensor]):
+    """tiling.py:201-224: per image, drop the patches whose UNDERSAMPLED version is black from both lists."""
+    for i in range(len(undersampled)):
+        keep = (ops.classify_patches(undersampled[i].to(torch.float32).contiguous()) == 0).nonzero(as_tuple=True)[0]
+        undersampled[i] = undersampled[i].index_select(0, keep)
+        fullysampled[i] = fullysampled[i].index_select(0, keep.to(fullysampled[i].device))
+    return undersampled, fullysampled
+
+
+def extract_center_batch(batch: torch.Tensor, outer_patch_size: int, inner_patch_size: int) -> torch.Tensor:
+    """tiling.py:306-322: the centre ``inner x inner`` window of every ``outer x outer`` patch (a view, as in the
+    reference; used for the training target, src/train/training.py:190-196)."""
+    padding = (outer_patch_size - inner_patch_size) // 2
+    return batch[:, padding: padding + inner_patch_size, padding: padding + inner_patch_size]

@@ -33,7 +33,9 @@ def _iteration(m, under, full, keep):
     m._train_keep_mask = keep
     m.zero_grad(set_to_none=True)
     out = m(under)
-    target = full[:, 4:28, 4:28].float()                                  # extract_center_batch(., 32, 24)
+    from mri_inr_b200.tiling import extract_center_batch
+
+    target = extract_center_batch(full, 32, 24).float()                   # training.py:190-196
     loss = torch.nn.functional.mse_loss(out, target)
     loss.backward()
     return out.detach(), float(loss.item()), {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
@@ -137,3 +139,18 @@ def test_optimizer_steps_reduce_the_loss():
         losses.append(float(loss.item()))
     print("losses", [round(x, 5) for x in losses])
     assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0]
+
+
+def test_training_side_tiling_helpers():
+    """filter_black_patches / filter_black_patches_indices / extract_center_batch (tiling.py:201-241,306-322), the
+    helpers src/train/training.py:18-25 and the dataset import."""
+    from mri_inr_b200 import tiling
+
+    u = torch.from_numpy(synth_tiles(3, 9)).to(DEV)        # patch 1 is black
+    u[4] = 0.0
+    f = torch.from_numpy(synth_tiles(4, 9)).to(DEV)
+    assert tiling.filter_black_patches_indices(u) == [0, 2, 3, 5, 6, 7, 8]
+    (fu,), (ff,) = tiling.filter_black_patches([u.clone()], [f.clone()])
+    assert fu.shape[0] == 7 and torch.equal(ff, f[[0, 2, 3, 5, 6, 7, 8]])
+    c = tiling.extract_center_batch(f, 32, 24)
+    assert c.shape == (9, 24, 24) and torch.equal(c, f[:, 4:28, 4:28])

@@ -466,6 +466,10 @@ def run_ours(args):
                        "black_patch_fraction": black_frac,
                        "black_patch_note": "1 - (patches the synthesis kernel computed, its device-side count) / (patches handed to it)",
                        "coords_per_s": value * PATCHES_PER_SLICE * COORDS_PER_PATCH * (1.0 - black_frac),
+                       "parity": "model + tiling path pinned against goldens of the unmodified reference; UNPINNED: the "
+                                 "k-space front end that makes the inputs (fastmri absent: checked against numpy fp64) "
+                                 "and PSNR/SSIM (scikit-image absent: checked against two independent fp64 "
+                                 "formulations) -- neither is inside the timed region",
                        "l2": f"inputs larger than L2 ({n_local * IMG * IMG * 4 / 1e6:.0f} MB of slices per rank per step; "
                              f"intermediates {chunk * 400 * (1024 + L * 256 + 576) * 4 / 1e6:.0f} MB per chunk)"},
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": n_total * IMG * IMG * 4,

@@ -292,7 +292,10 @@ def run_ours(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a rank that dies must turn into an error on the others within minutes, not into a silent hang
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     n_total = args.slices
     s0, s1 = shard_range(n_total, rank, world)
     n_local = s1 - s0

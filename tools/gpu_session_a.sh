@@ -4,8 +4,11 @@ cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/a_smi.txt 2>&1
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_multi.py > $O/a_pytest.log 2>&1; echo "rc=$?"; tail -15 $O/a_pytest.log
-echo "== remaining tests after first failure (if any)"; timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_gpu_multi.py > $O/a_pytest_all.log 2>&1; echo "rc=$?"; tail -30 $O/a_pytest_all.log | cut -c1-220
+# separate processes per group: a trapped kernel kills the CUDA context of its process only
+echo "== g1 parity (round-1 scope + Morlet envelope)"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "not fp16x3 and not auto and not hard_cases" > $O/a_g1.log 2>&1; echo "rc=$?"; tail -12 $O/a_g1.log | cut -c1-250
+echo "== g2 fp16x3 / auto / hard cases"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "fp16x3 or auto or hard_cases" > $O/a_g2.log 2>&1; echo "rc=$?"; grep -E "max-abs|auto ->|passed|failed|Error|error" $O/a_g2.log | tail -40 | cut -c1-250
+echo "== g3 training"; timeout 600 python -m pytest tests/test_gpu_train.py -m gpu -q -s > $O/a_g3.log 2>&1; echo "rc=$?"; tail -40 $O/a_g3.log | cut -c1-250
+echo "== g4 replay of test_mod_siren.py"; timeout 600 python -m pytest tests/test_replay_reference_script.py -m gpu -q > $O/a_g4.log 2>&1; echo "rc=$?"; tail -12 $O/a_g4.log | cut -c1-250
 echo "== bench sine"; timeout 300 python bench.py --steps 3 --warmup 3 > $O/a_bench_sine.json 2> $O/a_bench_sine.err; echo "rc=$?"; tail -c 900 $O/a_bench_sine.json; tail -2 $O/a_bench_sine.err
 echo "== bench morlet"; timeout 300 python bench.py --steps 3 --warmup 3 --activation morlet --no-cpu-baseline > $O/a_bench_morlet.json 2> $O/a_bench_morlet.err; echo "rc=$?"; tail -c 600 $O/a_bench_morlet.json; tail -2 $O/a_bench_morlet.err
 echo "== bench cfg4 (L=9, Z=128)"; timeout 300 python bench.py --steps 3 --warmup 3 --num-layers 9 --latent-dim 128 --no-cpu-baseline > $O/a_bench_cfg4.json 2> $O/a_bench_cfg4.err; echo "rc=$?"; tail -c 600 $O/a_bench_cfg4.json; tail -2 $O/a_bench_cfg4.err

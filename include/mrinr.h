@@ -104,6 +104,10 @@ MRINR_API void mrinr_free_packed(MrinrPacked* p);
 /* Copies the layer-0 table [C,H] fp32 to d_out (test/introspection hook). */
 MRINR_API int  mrinr_packed_layer0_table(const MrinrPacked* p, float* d_out, void* stream);
 
+/* The persistent synthesis kernel launches one CTA pair per SM pair (74 on a B200).  `clusters` > 0 caps that number,
+ * leaving SMs free for kernels of another stream (the front end of the next chunk); 0 restores the default. */
+MRINR_API int mrinr_set_synthesis_clusters(MrinrPacked* p, int32_t clusters);
+
 /* ---- coordinate grid: modulated_siren.py:427-433 -------------------------------------------------- */
 /* d_out [S*S,2]: out[c] = (lin[c / S], lin[c % S]), lin = torch.linspace(-1,1,S).  Bit-exact. */
 MRINR_API int mrinr_make_grid(int32_t S, float* d_out, void* stream);

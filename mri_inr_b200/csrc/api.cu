@@ -284,6 +284,12 @@ fail:
 #undef PK_RC
 }
 
+extern "C" int mrinr_set_synthesis_clusters(MrinrPacked* p, int32_t clusters) {
+  MRINR_REQUIRE(p && clusters >= 0, MRINR_E_ARG, "mrinr_set_synthesis_clusters: bad argument");
+  p->synth_clusters = clusters;
+  return 0;
+}
+
 extern "C" int mrinr_packed_layer0_table(const MrinrPacked* p, float* d_out, void* stream) {
   MRINR_REQUIRE(p && d_out, MRINR_E_ARG, "mrinr_packed_layer0_table: null argument");
   MRINR_CUDA(cudaMemcpyAsync(d_out, p->d_table0, (size_t)p->C * p->H * sizeof(float), cudaMemcpyDeviceToDevice,

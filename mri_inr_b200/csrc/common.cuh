@@ -65,6 +65,7 @@ struct MrinrPacked {
   int32_t activation, precision;
   int32_t device;
   int32_t num_sms;
+  int32_t synth_clusters;   // CTA pairs the synthesis kernel may use (0 = one per SM pair); mrinr_set_synthesis_clusters
   float*    d_table0;    // [C,H]  act_0(W_0 g_c + b_0), fp32 (before modulation)
   uint16_t* d_table16;   // [C,H]  the same table in the tensor-core operand format (fp16 / bf16)
   float*    d_net_wT;    // [(L-1)][H(k)][H(n)]  fp32 transposed hidden weights (fp32 mode)

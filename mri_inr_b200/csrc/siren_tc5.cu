@@ -763,6 +763,7 @@ int launch_siren_tc_v5(const MrinrPacked* p, const float* d_mods, const int32_t*
   // iteration processes 4 tiles -- 2 in the fp16x3 mode -- of the same coordinate block)
   const long long tpi = x3 ? 2 : 4;
   long long clusters = p->num_sms / 2;
+  if (p->synth_clusters > 0 && p->synth_clusters < clusters) clusters = p->synth_clusters;
   const long long groups = (B + tpi - 1) / tpi;
   if (clusters > groups) clusters = groups;
   if (clusters < 1) clusters = 1;

@@ -15,6 +15,7 @@ echo "== bench cfg4 (L=9, Z=128)"; timeout 300 python bench.py --steps 3 --warmu
 echo "== bench dense mods"; timeout 300 python bench.py --steps 3 --warmup 3 --mods dense --no-cpu-baseline > $O/a_bench_dense.json 2> $O/a_bench_dense.err; echo "rc=$?"; tail -c 600 $O/a_bench_dense.json; tail -2 $O/a_bench_dense.err
 echo "== bench fp16x3"; timeout 300 python bench.py --steps 2 --warmup 3 --precision fp16x3 --mods dense --no-cpu-baseline --slices 2068 > $O/a_bench_x3.json 2> $O/a_bench_x3.err; echo "rc=$?"; tail -c 600 $O/a_bench_x3.json; tail -2 $O/a_bench_x3.err
 echo "== precision table"; timeout 300 python tools/precision_table.py > $O/a_precision_table.txt 2>&1; echo "rc=$?"; cat $O/a_precision_table.txt
+echo "== SM sweep"; timeout 200 python tools/sm_sweep.py > $O/a_sm_sweep.txt 2>&1; echo "rc=$?"; cat $O/a_sm_sweep.txt
 echo "== power split"
 for v in default NO_MMA NO_SIN NO_BIAS NO_STS; do
   if [ $v = default ]; then timeout 120 python tools/power_split.py 60 >> $O/a_power.txt 2>&1; else MRINR_LIB=build/libmrinr_$v.so timeout 120 python tools/power_split.py 60 >> $O/a_power.txt 2>&1; fi

@@ -240,7 +240,7 @@ def siren_forward(packed: PackedWeights, mods: torch.Tensor, black: Optional[tor
 
 
 def image_to_patches(images: torch.Tensor, outer: int, inner: int, with_black_mask: bool = False,
-                     out: Optional[torch.Tensor] = None):
+                     out: Optional[torch.Tensor] = None, black_out: Optional[torch.Tensor] = None):
     """``image_to_patches`` (src/util/tiling.py:10-64) for a batch ``[N,H,W]`` of equally sized images.
     Returns ``(patches [N*nV*nH, outer, outer], (nV, nH), black_mask or None)``."""
     lib = _lib.load()
@@ -253,7 +253,9 @@ def image_to_patches(images: torch.Tensor, outer: int, inner: int, with_black_ma
     P = N * nV * nH
     if out is None:
         out = torch.empty(P, outer, outer, dtype=torch.float32, device=dev)
-    black = torch.empty(P, dtype=torch.uint8, device=dev) if with_black_mask else None
+    black = None
+    if with_black_mask:
+        black = torch.empty(P, dtype=torch.uint8, device=dev) if black_out is None else black_out[:P]
     with torch.cuda.device(dev):
         _lib.check(lib.mrinr_image_to_patches(images.data_ptr(), N, H, W, outer, inner, out.data_ptr(), _ptr(black),
                                               _lib.stream_ptr(dev)), "image_to_patches")

@@ -21,9 +21,12 @@ from .tiling import _weights_on
 
 
 class ReconstructionPipeline:
-    def __init__(self, model: ModulatedSiren, chunk_slices: int = 256):
+    def __init__(self, model: ModulatedSiren, chunk_slices: int = 256, overlap_clusters: int = 0):
+        """``overlap_clusters`` > 0: the synthesis kernel is capped to that many CTA pairs (of 74 on a B200) and the
+        front end of chunk i+1 runs on a side stream underneath the synthesis of chunk i (``reconstruct`` only)."""
         self.model = model
         self.chunk_slices = int(chunk_slices)
+        self.overlap_clusters = int(overlap_clusters)
         self._buf = {}
 
     def _buffer(self, name: str, shape, dtype, device) -> torch.Tensor:
@@ -38,43 +41,47 @@ class ReconstructionPipeline:
         return t[:numel].view(*shape)
 
     def _prepare(self, H: int, W: int, n_max: int, dev):
-        """Chunk-sized, reusable intermediates for images of H x W (allocated once per shape)."""
+        """Chunk-sized, reusable intermediates for images of H x W (allocated once per shape).  The buffers the front
+        end writes (patches, black mask, encoder scratch, latent, modulations) exist twice when the front end of the
+        next chunk overlaps the synthesis of the current one."""
         m = self.model
         O, I, S = m.outer_patch_size, m.inner_patch_size, m.siren_patch_size
         nV, nH = -(-H // I), -(-W // I)
         P = nV * nH
         packed = m._packed()
         cs = max(1, min(self.chunk_slices, n_max))
+        front = []
+        for k in range(2 if self.overlap_clusters > 0 else 1):
+            front.append(dict(
+                patches=self._buffer(f"patches{k}", (cs * P, O, O), torch.float32, dev),
+                black=self._buffer(f"black{k}", (cs * P,), torch.uint8, dev),
+                z=self._buffer(f"z{k}", (cs * P, packed.Z), torch.float32, dev),
+                mods=self._buffer(f"mods{k}", (packed.L * cs * P * packed.H,), torch.float32, dev),
+                enc_ws=(self._buffer(f"enc_ws{k}", (max(16, ops.encoder_workspace_bytes(cs * P)),), torch.uint8, dev)
+                        if packed.has_encoder else None)))
         bufs = dict(
-            patches=self._buffer("patches", (cs * P, O, O), torch.float32, dev),
-            mods=self._buffer("mods", (packed.L * cs * P * packed.H,), torch.float32, dev),
+            front=front,
             tiles=self._buffer("tiles", (cs * P, S, S), torch.float32, dev),
             ws=self._buffer("ws", (int(ops._lib.load().mrinr_siren_workspace_bytes(cs * P)),), torch.uint8, dev),
-            enc_ws=(self._buffer("enc_ws", (max(16, ops.encoder_workspace_bytes(cs * P)),), torch.uint8, dev)
-                    if packed.has_encoder else None),
             wts=_weights_on(S, dev),
         )
         return packed, cs, (nV, nH, P, O, I, S), bufs
 
-    def _chunk(self, images: torch.Tensor, out: torch.Tensor, packed, geom, bufs, skip_black: bool,
-               kernel_events: Optional[list]) -> None:
-        """One chunk of slices, a handful of launches on the current stream: images [n,H,W] -> out [n,nV*I,nH*I]."""
+    def _front(self, images: torch.Tensor, packed, geom, fb, skip_black: bool):
+        """Front end of one chunk on the current stream: images [n,H,W] -> (modulations [L,B,H], black mask [B])."""
         m = self.model
         nV, nH, P, O, I, S = geom
-        n = images.shape[0]
+        B = images.shape[0] * P
+        patches, _, black = ops.image_to_patches(images, O, I, with_black_mask=skip_black, out=fb["patches"][:B],
+                                                 black_out=fb["black"])
+        z = ops.encoder_forward(packed, patches, out=fb["z"][:B], workspace=fb["enc_ws"])
+        mods = ops.modulator_forward(packed, z, out=fb["mods"][: packed.L * B * packed.H].view(packed.L, B, packed.H))
+        return mods, black
+
+    def _back(self, mods, black, n: int, out: torch.Tensor, packed, geom, bufs, kernel_events: Optional[list]) -> None:
+        """Synthesis + weighted reassembly of one chunk on the current stream."""
+        nV, nH, P, O, I, S = geom
         B = n * P
-        if m.precision == "auto":
-            packed = m._packed()        # the handle is rebuilt when the self-check below changes the mode
-        patches, _, black = ops.image_to_patches(images, O, I, with_black_mask=skip_black, out=bufs["patches"][:B])
-        z = m.encoder(patches, workspace=bufs["enc_ws"])
-        mods = ops.modulator_forward(packed, z.contiguous(),
-                                     out=bufs["mods"][: packed.L * B * packed.H].view(packed.L, B, packed.H))
-        if m.precision == "auto":
-            # precision="auto": the first chunk's modulations decide the mode (one-off self-check against the fp32
-            # kernel, ModulatedSiren._resolve_auto); the handle may have been rebuilt, so fetch it again
-            if m._auto_key != m._weights_key():
-                m._resolve_auto(mods)
-            packed = m._packed()
         if kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -86,6 +93,21 @@ class ReconstructionPipeline:
             nact = bufs["ws"][:4].view(torch.int32).clone() if black is not None else None
             kernel_events.append((e0, e1, B, nact))
         ops.patches_to_image(tiles.view(B, S, S), n, (nV, nH), I, weights=bufs["wts"], black=black, out=out)
+
+    def _chunk(self, images: torch.Tensor, out: torch.Tensor, packed, geom, bufs, skip_black: bool,
+               kernel_events: Optional[list]) -> None:
+        """One chunk of slices, a handful of launches on the current stream: images [n,H,W] -> out [n,nV*I,nH*I]."""
+        m = self.model
+        if m.precision == "auto":
+            packed = m._packed()        # the handle is rebuilt when the self-check below changes the mode
+        mods, black = self._front(images, packed, geom, bufs["front"][0], skip_black)
+        if m.precision == "auto":
+            # precision="auto": the first chunk's modulations decide the mode (one-off self-check against the fp32
+            # kernel, ModulatedSiren._resolve_auto); the handle may have been rebuilt, so fetch it again
+            if m._auto_key != m._weights_key():
+                m._resolve_auto(mods)
+            packed = m._packed()
+        self._back(mods, black, images.shape[0], out, packed, geom, bufs, kernel_events)
 
     @torch.no_grad()
     def reconstruct(self, images: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -107,9 +129,49 @@ class ReconstructionPipeline:
         nV, nH, P, O, I, S = geom
         if out is None:
             out = torch.empty(N, nV * I, nH * I, dtype=torch.float32, device=dev)
-        for s0 in range(0, N, cs):
-            n = min(cs, N - s0)
-            self._chunk(images[s0:s0 + n], out[s0:s0 + n], packed, geom, bufs, skip_black, kernel_events)
+        starts = list(range(0, N, cs))
+        if self.overlap_clusters <= 0 or len(starts) < 2 or m.precision == "auto":
+            for s0 in starts:
+                n = min(cs, N - s0)
+                self._chunk(images[s0:s0 + n], out[s0:s0 + n], packed, geom, bufs, skip_black, kernel_events)
+            return out
+        # ---- front end of chunk i+1 on a side stream, underneath the synthesis kernel of chunk i.  The synthesis
+        # kernel is limited by the power cap, not by SM count (tools/sm_sweep.py), so it gives up a few SM pairs
+        # (mrinr_set_synthesis_clusters) and the front-end CTAs of the next chunk run on them.
+        lib = ops._lib.load()
+        main = torch.cuda.current_stream(dev)
+        if "front_stream" not in self._buf:
+            self._buf["front_stream"] = torch.cuda.Stream(dev, priority=0)
+        side = self._buf["front_stream"]
+        lib.mrinr_set_synthesis_clusters(packed.handle, self.overlap_clusters)
+        try:
+            ev_front = [torch.cuda.Event() for _ in starts]
+            ev_back = [torch.cuda.Event() for _ in starts]
+            start = torch.cuda.Event()
+            start.record(main)
+            side.wait_event(start)
+            results = {}
+
+            def front(i):
+                s0 = starts[i]
+                n = min(cs, N - s0)
+                with torch.cuda.stream(side):
+                    if i >= 2:
+                        side.wait_event(ev_back[i - 2])          # chunk i-2 no longer reads this buffer set
+                    results[i] = self._front(images[s0:s0 + n], packed, geom, bufs["front"][i & 1], skip_black)
+                    ev_front[i].record(side)
+
+            front(0)
+            for i, s0 in enumerate(starts):
+                n = min(cs, N - s0)
+                if i + 1 < len(starts):
+                    front(i + 1)
+                main.wait_event(ev_front[i])
+                mods, black = results.pop(i)
+                self._back(mods, black, n, out[s0:s0 + n], packed, geom, bufs, kernel_events)
+                ev_back[i].record(main)
+        finally:
+            lib.mrinr_set_synthesis_clusters(packed.handle, 0)
         return out
 
     @torch.no_grad()

@@ -796,3 +796,24 @@ def test_image_metrics_match_direct_window_formulation(hw):
         want = ometrics.ssim_direct(full[i], pred[i])
         print(f"{hw} pair {i}: ssim {got[i, 1]:.9f} direct {want:.9f}")
         assert abs(got[i, 1] - want) <= 1e-4
+
+
+def test_front_end_overlap_is_bit_identical():
+    """ReconstructionPipeline(overlap_clusters=k): the front end of chunk i+1 on a side stream underneath the synthesis of
+    chunk i (double-buffered patches / modulations, synthesis kernel capped to k CTA pairs) gives bit-identical slices,
+    with an odd number of chunks and a ragged last one."""
+    from mri_inr_b200.pipeline import ReconstructionPipeline
+    from mri_inr_b200.synthetic import synthetic_slices
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    imgs = synthetic_slices(23, 320, 320, device=DEV, seed=5)
+    want = ReconstructionPipeline(m, chunk_slices=5).reconstruct(imgs)
+    for k in (64, 70):
+        got = ReconstructionPipeline(m, chunk_slices=5, overlap_clusters=k).reconstruct(imgs)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), k
+    ev = []
+    got = ReconstructionPipeline(m, chunk_slices=5, overlap_clusters=66).reconstruct(imgs, kernel_events=ev)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and len(ev) == 5

@@ -10,6 +10,7 @@ echo "== g2 fp16x3 / auto / hard cases"; timeout 600 python -m pytest tests/test
 echo "== g3 training"; timeout 600 python -m pytest tests/test_gpu_train.py -m gpu -q -s > $O/a_g3.log 2>&1; echo "rc=$?"; tail -40 $O/a_g3.log | cut -c1-250
 echo "== g4 replay of test_mod_siren.py"; timeout 600 python -m pytest tests/test_replay_reference_script.py -m gpu -q > $O/a_g4.log 2>&1; echo "rc=$?"; tail -12 $O/a_g4.log | cut -c1-250
 echo "== bench sine"; timeout 300 python bench.py --steps 3 --warmup 3 > $O/a_bench_sine.json 2> $O/a_bench_sine.err; echo "rc=$?"; tail -c 900 $O/a_bench_sine.json; tail -2 $O/a_bench_sine.err
+for k in 70 66 62; do echo "== bench sine, front end overlapped, $k CTA pairs"; timeout 300 python bench.py --steps 3 --warmup 3 --overlap-clusters $k --no-cpu-baseline --no-burst > $O/a_bench_ov$k.json 2> $O/a_bench_ov$k.err; echo "rc=$?"; python -c "import json;d=json.load(open('$O/a_bench_ov$k.json'));print(d['value'],d['roofline']['achieved'],d['roofline']['kernel_share_of_step'],d['clocks'])"; tail -2 $O/a_bench_ov$k.err; done
 echo "== bench morlet"; timeout 300 python bench.py --steps 3 --warmup 3 --activation morlet --no-cpu-baseline > $O/a_bench_morlet.json 2> $O/a_bench_morlet.err; echo "rc=$?"; tail -c 600 $O/a_bench_morlet.json; tail -2 $O/a_bench_morlet.err
 echo "== bench cfg4 (L=9, Z=128)"; timeout 300 python bench.py --steps 3 --warmup 3 --num-layers 9 --latent-dim 128 --no-cpu-baseline > $O/a_bench_cfg4.json 2> $O/a_bench_cfg4.err; echo "rc=$?"; tail -c 600 $O/a_bench_cfg4.json; tail -2 $O/a_bench_cfg4.err
 echo "== bench dense mods"; timeout 300 python bench.py --steps 3 --warmup 3 --mods dense --no-cpu-baseline > $O/a_bench_dense.json 2> $O/a_bench_dense.err; echo "rc=$?"; tail -c 600 $O/a_bench_dense.json; tail -2 $O/a_bench_dense.err

@@ -203,7 +203,9 @@ MRINR_API int mrinr_image_metrics(const float* d_original, const float* d_predic
  *   kept values scaled by 1/(1-p); d_keep_mask (optional, uint8 [L][B*C][H], 1 = keep) replaces the hash.
  * mrinr_train_backward: d_dout [B,C] = d(loss)/d(out).  `grads` reuses the MrinrWeightsView layout: every non-null
  *   pointer is a ZERO-INITIALISED, writable fp32 buffer of the parameter's shape that receives d(loss)/d(parameter)
- *   (accumulated with atomics); the scalar fields and d_grid are ignored.
+ *   (accumulated with atomics); the scalar fields and d_grid are ignored.  `grad_scale`: a power of two that brings
+ *   max|d_dout| * grad_scale to ~2^10 (the tensor-core products split their operands into fp16 halves, which resolve
+ *   22 bits only above 6e-5); applied to d_dout on the way in and divided out of the results.  1.0 = no scaling.
  * Requires dim_hidden 256, latent_dim in {64,128,256}, an encoder in `p`.  fp32-class arithmetic throughout. */
 MRINR_API int64_t mrinr_train_workspace_bytes(const MrinrPacked* p, int64_t B);
 MRINR_API int mrinr_train_forward(const MrinrPacked* p, const MrinrWeightsView* weights, const float* d_tiles, int64_t B,
@@ -211,8 +213,8 @@ MRINR_API int mrinr_train_forward(const MrinrPacked* p, const MrinrWeightsView* 
                                   void* d_workspace, int64_t workspace_bytes, void* stream);
 MRINR_API int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView* weights, const float* d_tiles,
                                    const float* d_dout, int64_t B, float dropout_p, uint64_t seed,
-                                   const uint8_t* d_keep_mask, const MrinrWeightsView* grads, void* d_workspace,
-                                   int64_t workspace_bytes, void* stream);
+                                   const uint8_t* d_keep_mask, float grad_scale, const MrinrWeightsView* grads,
+                                   void* d_workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- peer memory for the one exchange step (gather of reconstructed slices to one rank) ---- */
 /* The reference has no distributed code; the multi-GPU sweep gathers every rank's reconstructed slices on one rank.

@@ -125,7 +125,8 @@ def _declare(lib: ctypes.CDLL) -> None:
                                         c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     lib.mrinr_train_backward.restype = c_int
     lib.mrinr_train_backward.argtypes = [c_void_p, POINTER(WeightsView), c_void_p, c_void_p, c_int64, c_float,
-                                         ctypes.c_uint64, c_void_p, POINTER(WeightsView), c_void_p, c_int64, c_void_p]
+                                         ctypes.c_uint64, c_void_p, c_float, POINTER(WeightsView), c_void_p, c_int64,
+                                         c_void_p]
 
 
 def load() -> ctypes.CDLL:

@@ -120,6 +120,9 @@ int launch_encoder_conv(const float* d_patches, long long B, const float* w1, co
                         const float* b2, float* d_out, int num_sms, cudaStream_t st);
 int launch_encoder_conv_tc(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,
                            const float* b2, float* d_out, int num_sms, int32_t* errflag, cudaStream_t st);
+int64_t wgrad_tc_scratch_floats(int num_sms);
+int launch_wgrad_tc(const float* dz, const float* h, long long M, float* scratch, float* dW, int num_sms,
+                    int32_t* errflag, cudaStream_t st);
 int launch_compact_black(const uint8_t* d_black, int64_t B, int32_t C, int32_t* d_idx, int32_t* d_nactive,
                          int32_t* d_blocksums, float* d_out, cudaStream_t st);
 

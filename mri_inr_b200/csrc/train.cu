@@ -12,9 +12,14 @@
 //
 // Arithmetic: everything is evaluated in fp32-class precision.  The [M,256] x [256,256] products of the forward and of
 // dh = dz W run on the tensor cores through the split-fp16 kernel of dense_tc.cu (three MMAs per product, ~1e-6);
-// the weight gradients dz^T h (a reduction over M = B * S * S rows) run on a CUDA-core split-K SGEMM with fp32
-// atomics, as do the small modulator / encoder gradients.  This is the correctness slice of the training path: the
-// reference trains under fp16 autocast (training.py:29,197), so fp32-class results are inside its own noise.
+// the weight gradients of the synthesis layers, dz^T h (a reduction over M = B * S * S rows), too (wgrad_tc.cu: the
+// reduction index is the MMA's K, the operand tiles are transposed while staging, split-K over the SMs).  The small
+// modulator / encoder weight gradients (a reduction over B rows) run on a CUDA-core split-K SGEMM with fp32 atomics.
+// The reference trains under fp16 autocast (training.py:29,197), so fp32-class results are inside its own noise.
+// Gradient range: the split-fp16 operands hold 22 significant bits only above ~6e-5 (fp16 subnormals below), and the
+// gradients of an MSE over B * S * S pixels are ~1e-6.  mrinr_train_backward therefore takes a power-of-two `grad_scale`
+// (the caller picks it from max|dy|, like a loss scale but exact): dy is multiplied by it on the way in, every
+// intermediate gradient carries it, and the parameter gradients are multiplied by 1/grad_scale at the end.
 // Dropout: counter-based (a hash of seed, layer and element index), recomputed in the backward pass -- no mask is
 // stored; an explicit keep-mask can be supplied instead (parity tests against the reference with a fixed mask).
 #include "common.cuh"
@@ -127,15 +132,15 @@ __global__ void out_fwd_kernel(const float* __restrict__ h, const float* __restr
 // one CTA per patch, thread = feature j:  g = dy w0 cos(w0 pre_last);  dh = g w_last;  dw_last += g h;  db_last += g
 __global__ void __launch_bounds__(kH) out_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre_last,
                                                      const float* __restrict__ h, const float* __restrict__ w_last, int C,
-                                                     float w0, float* __restrict__ dh, float* __restrict__ dw_last,
-                                                     float* __restrict__ db_last) {
+                                                     float w0, float grad_scale, float* __restrict__ dh,
+                                                     float* __restrict__ dw_last, float* __restrict__ db_last) {
   const long long b = blockIdx.x;
   const int j = threadIdx.x;
   const float wl = w_last[j];
   float accw = 0.f, accb = 0.f;
   for (int c = 0; c < C; ++c) {
     const long long m = b * C + c;
-    const float g = dy[m] * w0 * cosf(w0 * pre_last[m]);
+    const float g = dy[m] * grad_scale * w0 * cosf(w0 * pre_last[m]);
     dh[m * kH + j] = g * wl;
     accw = fmaf(g, h[m * kH + j], accw);
     accb += g;
@@ -291,6 +296,10 @@ __global__ void lrelu_bwd_kernel(float* __restrict__ D, const float* __restrict_
   if (i >= n) return;
   if (!(out[i] > 0.f)) D[i] *= slope;
 }
+__global__ void scale_kernel(float* __restrict__ Y, long long n, float s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) Y[i] *= s;
+}
 __global__ void add_kernel(float* __restrict__ Y, const float* __restrict__ X, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) Y[i] += X[i];
@@ -443,7 +452,7 @@ static int pack_split_strided(const float* src, int N, int K, long long sn, long
 // ---- workspace ---------------------------------------------------------------------------------------------------
 struct Ws {
   // element offsets (floats) into the workspace; every section starts at a multiple of 64 floats (256 bytes)
-  size_t enc, z, mods, pre0, h, pre, pre_last, pk, dA, dB, dmods, G, carry, dzlat, tmpz, dc3, dc2, total;
+  size_t enc, z, mods, pre0, h, pre, pre_last, pk, dA, dB, dmods, G, carry, dzlat, tmpz, dc3, dc2, wg, total;
   size_t plane;   // M * H
 };
 static inline size_t al(size_t x) { return (x + 63) & ~(size_t)63; }
@@ -471,6 +480,7 @@ static Ws layout(const MrinrPacked* p, int64_t B) {
   w.tmpz = o; o += al((size_t)B * (Z > 64 ? Z : 64));
   w.dc3 = o; o += al((size_t)B * 64);
   w.dc2 = o; o += al((size_t)B * 2048);
+  w.wg = o; o += al((size_t)wgrad_tc_scratch_floats(p->num_sms));      // per-CTA partial results of the weight gradient
   w.total = o;
   return w;
 }
@@ -562,10 +572,11 @@ extern "C" int mrinr_train_forward(const MrinrPacked* p, const MrinrWeightsView*
 // (null = not wanted).  d_grid is ignored (the grid is a buffer, not a parameter).
 extern "C" int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView* v, const float* d_tiles,
                                     const float* d_dout, int64_t B, float dropout_p, uint64_t seed,
-                                    const uint8_t* d_keep_mask, const MrinrWeightsView* grads, void* d_workspace,
-                                    int64_t workspace_bytes, void* stream) {
+                                    const uint8_t* d_keep_mask, float grad_scale, const MrinrWeightsView* grads,
+                                    void* d_workspace, int64_t workspace_bytes, void* stream) {
   if (B == 0) return 0;
   MRINR_REQUIRE(p && v && d_tiles && d_dout && grads && d_workspace, MRINR_E_ARG, "mrinr_train_backward: null pointer");
+  MRINR_REQUIRE(grad_scale > 0.f && grad_scale < 3e38f, MRINR_E_ARG, "mrinr_train_backward: grad_scale must be positive");
   int rc = check_cfg(p, "mrinr_train_backward");
   if (rc != 0) return rc;
   MRINR_REQUIRE(B > 0 && workspace_bytes >= mrinr_train_workspace_bytes(p, B), MRINR_E_ARG,
@@ -591,7 +602,8 @@ extern "C" int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView
   float* cur = ws + w.dA;      // gradient w.r.t. h_l, then (in place) w.r.t. the pre-activation of layer l
   float* nxt = ws + w.dB;
   out_bwd_kernel<<<(unsigned)B, kH, 0, st>>>(d_dout, ws + w.pre_last, ws + w.h + (size_t)(L - 1) * hs, v->d_last_weight,
-                                            C, p->w0, cur, (float*)grads->d_last_weight, (float*)grads->d_last_bias);
+                                            C, p->w0, grad_scale, cur, (float*)grads->d_last_weight,
+                                            (float*)grads->d_last_bias);
   count_launch();
   if ((rc = check_launch("out_bwd")) != 0) return rc;
   // ---- synthesis layers L-1 .. 0
@@ -604,9 +616,15 @@ extern "C" int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView
     count_launch();
     if ((rc = check_launch("act_bwd")) != 0) return rc;
     if (l == 0) break;
-    // dW_l[n][k] += sum_m dz[m][n] h_{l-1}[m][k]
+    // dW_l[n][k] += sum_m dz[m][n] h_{l-1}[m][k]: the big reduction (M rows) on the tensor cores (wgrad_tc.cu)
+#ifdef MRINR_WGRAD_SGEMM   // diagnostic build only (make wgsgemm): the CUDA-core split-K SGEMM instead
     if (g_net_w && g_net_w[l])
       if ((rc = gemm_tn_atomic(cur, kH, kH, ws + w.h + (size_t)(l - 1) * hs, kH, kH, M, g_net_w[l], kH, st)) != 0) return rc;
+#else
+    if (g_net_w && g_net_w[l])
+      if ((rc = launch_wgrad_tc(cur, ws + w.h + (size_t)(l - 1) * hs, M, ws + w.wg, g_net_w[l], p->num_sms, p->d_errflag,
+                                st)) != 0) return rc;
+#endif
     // dh_{l-1} = dz W_l : the packed operand is W_l^T, rows = k (output column), K index = n
     if ((rc = pack_split_strided(v->d_net_weight[l], kH, kH, 1, kH, pk, st)) != 0) return rc;
     rc = launch_dense_split(cur, kH, kH, nullptr, 0, 0, pk, nullptr, kH, 0, 0.f, nxt, kH, M, p->d_errflag, st);
@@ -679,6 +697,25 @@ extern "C" int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView
                                                      (float*)grads->d_enc_conv2_bias);
     count_launch();
     if ((rc = check_launch("encoder_conv_bwd")) != 0) return rc;
+  }
+  // ---- undo the gradient scale (exact: a power of two)
+  if (grad_scale != 1.f) {
+    const float inv = 1.f / grad_scale;
+    const int H = kH;
+    for (int l = 0; l < L; ++l) {
+      if (g_net_w && g_net_w[l]) EW_LAUNCH(scale_kernel, (long long)H * (l == 0 ? 2 : H), g_net_w[l], (long long)H * (l == 0 ? 2 : H), inv);
+      if (g_net_b && g_net_b[l]) EW_LAUNCH(scale_kernel, (long long)H, g_net_b[l], (long long)H, inv);
+      if (g_mod_w && g_mod_w[l]) EW_LAUNCH(scale_kernel, (long long)H * (l == 0 ? Z : H + Z), g_mod_w[l], (long long)H * (l == 0 ? Z : H + Z), inv);
+      if (g_mod_b && g_mod_b[l]) EW_LAUNCH(scale_kernel, (long long)H, g_mod_b[l], (long long)H, inv);
+    }
+    if (grads->d_last_weight) EW_LAUNCH(scale_kernel, (long long)H, (float*)grads->d_last_weight, (long long)H, inv);
+    if (grads->d_last_bias) EW_LAUNCH(scale_kernel, 1LL, (float*)grads->d_last_bias, 1LL, inv);
+    float* enc[8] = {(float*)grads->d_enc_conv1_weight, (float*)grads->d_enc_conv1_bias, (float*)grads->d_enc_conv2_weight,
+                     (float*)grads->d_enc_conv2_bias,   (float*)grads->d_enc_conv3_weight, (float*)grads->d_enc_conv3_bias,
+                     (float*)grads->d_enc_fc_weight,    (float*)grads->d_enc_fc_bias};
+    const long long encn[8] = {144, 16, 4608, 32, 64LL * 2048, 64, (long long)Z * 64, Z};
+    for (int i = 0; i < 8; ++i)
+      if (enc[i]) EW_LAUNCH(scale_kernel, encn[i], enc[i], encn[i], inv);
   }
   return 0;
 }

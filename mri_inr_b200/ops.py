@@ -428,12 +428,20 @@ def train_backward(packed: PackedWeights, view, grads_view, tiles: torch.Tensor,
                    seed: int, keep_mask: Optional[torch.Tensor], workspace: torch.Tensor) -> None:
     """Backward of :func:`train_forward`: ``dout [B, S*S]`` -> gradients accumulated into the zero-initialised
     buffers of ``grads_view`` (a ``weights_view`` over gradient tensors)."""
+    import math
+
     lib = _lib.load()
     _lib.require_cuda(dout, "dout", torch.float32)
     B = tiles.shape[0]
+    # exact power-of-two gradient scale (see include/mrinr.h): max|dout| * scale ~ 2^10.  One 4-byte read-back per
+    # iteration (the reference's loop reads loss.item() every iteration anyway, training.py:204).
+    amax = float(dout.abs().max())
+    grad_scale = 1.0
+    if math.isfinite(amax) and amax > 0.0:
+        grad_scale = 2.0 ** max(-100, min(100, 10 - math.ceil(math.log2(amax))))
     with torch.cuda.device(tiles.device):
         _lib.check(lib.mrinr_train_backward(packed.handle, ctypes.byref(view), tiles.data_ptr(), dout.data_ptr(), B,
                                             float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(keep_mask),
-                                            ctypes.byref(grads_view), workspace.data_ptr(),
+                                            float(grad_scale), ctypes.byref(grads_view), workspace.data_ptr(),
                                             workspace.numel() * workspace.element_size(),
                                             _lib.stream_ptr(tiles.device)), "train_backward")

@@ -8,6 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 echo "== g1 parity (round-1 scope + Morlet envelope)"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "not fp16x3 and not auto and not hard_cases" > $O/a_g1.log 2>&1; echo "rc=$?"; tail -12 $O/a_g1.log | cut -c1-250
 echo "== g2 fp16x3 / auto / hard cases"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "fp16x3 or auto or hard_cases" > $O/a_g2.log 2>&1; echo "rc=$?"; grep -E "max-abs|auto ->|passed|failed|Error|error" $O/a_g2.log | tail -40 | cut -c1-250
 echo "== diag train"; timeout 300 python tools/diag_train.py > $O/a_diag_train.txt 2>&1; echo "rc=$?"; cat $O/a_diag_train.txt | cut -c1-200
+echo "== diag train, SGEMM weight gradient (diagnostic build)"; MRINR_LIB=build/libmrinr_wgsgemm.so timeout 300 python tools/diag_train.py > $O/a_diag_train_sgemm.txt 2>&1; echo "rc=$?"; grep -E "===|forward|<<<<|Error|error" $O/a_diag_train_sgemm.txt | cut -c1-200
 echo "== g3 training"; timeout 600 python -m pytest tests/test_gpu_train.py -m gpu -q -s > $O/a_g3.log 2>&1; echo "rc=$?"; tail -40 $O/a_g3.log | cut -c1-250
 echo "== g4 replay of test_mod_siren.py"; timeout 600 python -m pytest tests/test_replay_reference_script.py -m gpu -q > $O/a_g4.log 2>&1; echo "rc=$?"; tail -12 $O/a_g4.log | cut -c1-250
 echo "== bench sine"; timeout 300 python bench.py --steps 3 --warmup 3 > $O/a_bench_sine.json 2> $O/a_bench_sine.err; echo "rc=$?"; tail -c 900 $O/a_bench_sine.json; tail -2 $O/a_bench_sine.err

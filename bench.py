@@ -307,7 +307,7 @@ def run_ours(args):
     model, sd = build_state_dict(args.activation, num_layers=L, latent_dim=args.latent_dim, mods=args.mods)
     model.to(dev).eval()
     model.precision = args.precision
-    pipe = ReconstructionPipeline(model, chunk_slices=chunk, overlap_clusters=args.overlap_clusters)
+    pipe = ReconstructionPipeline(model, chunk_slices=chunk)
 
     # synthetic undersampled slices of this rank's block (set-up, untimed); seeds depend on the global index
     images = synthetic_slices(n_local, IMG, IMG, device=dev, seed=1234 + s0)
@@ -462,8 +462,7 @@ def run_ours(args):
                                    f"940-volume-shaped set: {n_total} slices 320x320 (acc 6 / cf 0.05), "
                                    f"{args.mods} weights; patches -> encoder -> modulator -> fused tcgen05 MLP -> "
                                    f"weighted reassembly",
-                       "slices": n_total, "chunk_slices": chunk, "front_end_overlap_clusters": args.overlap_clusters,
-                       "num_layers": L, "latent_dim": args.latent_dim,
+                       "slices": n_total, "chunk_slices": chunk, "num_layers": L, "latent_dim": args.latent_dim,
                        "activation": args.activation, "modulations": args.mods,
                        "parallelism": f"slices block-partitioned x{world}", "exchange": exchange,
                        "precision": f"{prec} operands, fp32 accumulate" + (f" (requested: {args.precision})" if prec != args.precision else ""),
@@ -537,9 +536,6 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16x3", "bf16", "fp32", "auto"])
     ap.add_argument("--slices", type=int, default=N_SLICES)
     ap.add_argument("--chunk", type=int, default=0, help="slices per launch; 0 = near 235, dividing the per-rank block evenly")
-    ap.add_argument("--overlap-clusters", type=int, default=0,
-                    help="> 0: cap the synthesis kernel to this many CTA pairs (of 74) and run the front end of the next "
-                         "chunk on a side stream underneath it (see ReconstructionPipeline)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--ref-slices", type=int, default=4, help="slices per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -130,6 +130,24 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
   }
 }
 
+// Morlet envelope exp(-x^2/2) of two activations of group g (0..3) of a 16-activation chunk.  The special-function unit
+// (one MUFU.SIN per activation already) and the FMA pipe are both close to their limits in the Morlet epilogue, so the
+// envelope is split between them: groups whose bit is set in kMorletFmaMask use the FMA-pipe evaluation (gauss2),
+// the others ex2.approx on the special-function unit.  Measured (profiles/r02_morlet_variants.txt).
+#ifndef MRINR_MORLET_FMA_MASK
+#define MRINR_MORLET_FMA_MASK 0xF
+#endif
+constexpr int kMorletFmaMask = MRINR_MORLET_FMA_MASK;
+__device__ __forceinline__ uint64_t morlet_env2(int g, float x0, float x1) {
+  if ((kMorletFmaMask >> g) & 1) return gauss2(x0, x1);
+  float t0, t1;
+  upk2(vmul2(pk2(x0, x1), pk2(x0, x1)), t0, t1);
+  float e0, e1;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0 * -0.72134752044448170368f));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1 * -0.72134752044448170368f));
+  return pk2(e0, e1);
+}
+
 template <int ACT, int PREC, bool W0ONE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_tc5_kernel(const SirenTcParams P) {
   constexpr bool BF16 = (PREC == MRINR_PREC_BF16);
@@ -264,9 +282,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         } else {
           // Morlet (modulated_siren.py:80): sin(w0 x) exp(-x^2/2).  One MUFU.SIN per activation as for sine; the
           // envelope runs on the FMA pipe as packed pairs (gauss2) underneath the next group's sines.
-          const uint64_t h01 = vmul2(gauss2(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1])),
+          const uint64_t h01 = vmul2(morlet_env2(g, __uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1])),
                                      vmul2(pk2(s[g * 4 + 0], s[g * 4 + 1]), pk2(mm.x, mm.y)));
-          const uint64_t h23 = vmul2(gauss2(__uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])),
+          const uint64_t h23 = vmul2(morlet_env2(g, __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])),
                                      vmul2(pk2(s[g * 4 + 2], s[g * 4 + 3]), pk2(mm.z, mm.w)));
           float a0, a1, a2, a3;
           upk2(h01, a0, a1);
@@ -280,7 +298,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float x = __uint_as_float(v[g * 4 + i]);
-          s[g * 4 + i] = vsin_live(W0ONE ? x : P.w0 * x, mg[i]);
+          // X3 is the accuracy mode and waits for the tensor core anyway: full-precision sine there (sin.approx's 2^-21
+          // absolute error, amplified by large weights, was the mode's error floor: 6e-4 at W x 3)
+          s[g * 4 + i] = X3 ? sin_accurate(W0ONE ? x : P.w0 * x) : vsin_live(W0ONE ? x : P.w0 * x, mg[i]);
         }
         if (g > 0) finish_group(g - 1);
       }
@@ -332,16 +352,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         for (int g = 0; g < 4; ++g) {
           const float x0 = __uint_as_float(v[g * 4 + 0]), x1 = __uint_as_float(v[g * 4 + 1]);
           const float x2 = __uint_as_float(v[g * 4 + 2]), x3 = __uint_as_float(v[g * 4 + 3]);
-          const float h0 = vsin_live(W0ONE ? x0 : P.w0 * x0, mw[g].x), h1 = vsin_live(W0ONE ? x1 : P.w0 * x1, mw[g].y);
-          const float h2 = vsin_live(W0ONE ? x2 : P.w0 * x2, mw[g].z), h3 = vsin_live(W0ONE ? x3 : P.w0 * x3, mw[g].w);
+          float h0, h1, h2, h3;
+          if (X3) {
+            h0 = sin_accurate(W0ONE ? x0 : P.w0 * x0); h1 = sin_accurate(W0ONE ? x1 : P.w0 * x1);
+            h2 = sin_accurate(W0ONE ? x2 : P.w0 * x2); h3 = sin_accurate(W0ONE ? x3 : P.w0 * x3);
+          } else {
+            h0 = vsin_live(W0ONE ? x0 : P.w0 * x0, mw[g].x); h1 = vsin_live(W0ONE ? x1 : P.w0 * x1, mw[g].y);
+            h2 = vsin_live(W0ONE ? x2 : P.w0 * x2, mw[g].z); h3 = vsin_live(W0ONE ? x3 : P.w0 * x3, mw[g].w);
+          }
           if (ACT == MRINR_ACT_SINE) {
             d0 = fmaf(h0, mw[g].x, d0);
             d1 = fmaf(h1, mw[g].y, d1);
             d2 = fmaf(h2, mw[g].z, d2);
             d3 = fmaf(h3, mw[g].w, d3);
           } else {
-            d01 = vfma2(vmul2(gauss2(x0, x1), pk2(h0, h1)), pk2(mw[g].x, mw[g].y), d01);
-            d23 = vfma2(vmul2(gauss2(x2, x3), pk2(h2, h3)), pk2(mw[g].z, mw[g].w), d23);
+            d01 = vfma2(vmul2(morlet_env2(g, x0, x1), pk2(h0, h1)), pk2(mw[g].x, mw[g].y), d01);
+            d23 = vfma2(vmul2(morlet_env2(g, x2, x3), pk2(h2, h3)), pk2(mw[g].z, mw[g].w), d23);
           }
         }
       };

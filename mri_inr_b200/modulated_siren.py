@@ -218,7 +218,8 @@ class ModulatedSiren(nn.Module):
 
     The default can be set with the environment variable ``MRINR_PRECISION``."""
 
-    AUTO_TOLERANCE = 2.5e-4      # max-abs against the fp32 kernel: a factor 4 under north_star's 1e-3
+    AUTO_TOLERANCE = 5e-4        # max-abs against the fp32 kernel on the sample: a factor 2 under north_star's 1e-3
+                                 # (trained-like baseline-scale weights sit at 2e-4 .. 4e-4 in fp16 and keep the fast path)
     AUTO_SAMPLE = 256            # patches of the first batch used by the self-check
 
     def __init__(self, dim_in, dim_hidden, dim_out, num_layers, latent_dim, w0, w0_initial, use_bias, dropout,

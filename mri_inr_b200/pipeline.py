@@ -21,12 +21,9 @@ from .tiling import _weights_on
 
 
 class ReconstructionPipeline:
-    def __init__(self, model: ModulatedSiren, chunk_slices: int = 256, overlap_clusters: int = 0):
-        """``overlap_clusters`` > 0: the synthesis kernel is capped to that many CTA pairs (of 74 on a B200) and the
-        front end of chunk i+1 runs on a side stream underneath the synthesis of chunk i (``reconstruct`` only)."""
+    def __init__(self, model: ModulatedSiren, chunk_slices: int = 256):
         self.model = model
         self.chunk_slices = int(chunk_slices)
-        self.overlap_clusters = int(overlap_clusters)
         self._buf = {}
 
     def _buffer(self, name: str, shape, dtype, device) -> torch.Tensor:
@@ -41,9 +38,7 @@ class ReconstructionPipeline:
         return t[:numel].view(*shape)
 
     def _prepare(self, H: int, W: int, n_max: int, dev):
-        """Chunk-sized, reusable intermediates for images of H x W (allocated once per shape).  The buffers the front
-        end writes (patches, black mask, encoder scratch, latent, modulations) exist twice when the front end of the
-        next chunk overlaps the synthesis of the current one."""
+        """Chunk-sized, reusable intermediates for images of H x W (allocated once per shape)."""
         m = self.model
         O, I, S = m.outer_patch_size, m.inner_patch_size, m.siren_patch_size
         nV, nH = -(-H // I), -(-W // I)
@@ -51,7 +46,7 @@ class ReconstructionPipeline:
         packed = m._packed()
         cs = max(1, min(self.chunk_slices, n_max))
         front = []
-        for k in range(2 if self.overlap_clusters > 0 else 1):
+        for k in range(1):
             front.append(dict(
                 patches=self._buffer(f"patches{k}", (cs * P, O, O), torch.float32, dev),
                 black=self._buffer(f"black{k}", (cs * P,), torch.uint8, dev),
@@ -129,49 +124,9 @@ class ReconstructionPipeline:
         nV, nH, P, O, I, S = geom
         if out is None:
             out = torch.empty(N, nV * I, nH * I, dtype=torch.float32, device=dev)
-        starts = list(range(0, N, cs))
-        if self.overlap_clusters <= 0 or len(starts) < 2 or m.precision == "auto":
-            for s0 in starts:
-                n = min(cs, N - s0)
-                self._chunk(images[s0:s0 + n], out[s0:s0 + n], packed, geom, bufs, skip_black, kernel_events)
-            return out
-        # ---- front end of chunk i+1 on a side stream, underneath the synthesis kernel of chunk i.  The synthesis
-        # kernel is limited by the power cap, not by SM count (tools/sm_sweep.py), so it gives up a few SM pairs
-        # (mrinr_set_synthesis_clusters) and the front-end CTAs of the next chunk run on them.
-        lib = ops._lib.load()
-        main = torch.cuda.current_stream(dev)
-        if "front_stream" not in self._buf:
-            self._buf["front_stream"] = torch.cuda.Stream(dev, priority=0)
-        side = self._buf["front_stream"]
-        lib.mrinr_set_synthesis_clusters(packed.handle, self.overlap_clusters)
-        try:
-            ev_front = [torch.cuda.Event() for _ in starts]
-            ev_back = [torch.cuda.Event() for _ in starts]
-            start = torch.cuda.Event()
-            start.record(main)
-            side.wait_event(start)
-            results = {}
-
-            def front(i):
-                s0 = starts[i]
-                n = min(cs, N - s0)
-                with torch.cuda.stream(side):
-                    if i >= 2:
-                        side.wait_event(ev_back[i - 2])          # chunk i-2 no longer reads this buffer set
-                    results[i] = self._front(images[s0:s0 + n], packed, geom, bufs["front"][i & 1], skip_black)
-                    ev_front[i].record(side)
-
-            front(0)
-            for i, s0 in enumerate(starts):
-                n = min(cs, N - s0)
-                if i + 1 < len(starts):
-                    front(i + 1)
-                main.wait_event(ev_front[i])
-                mods, black = results.pop(i)
-                self._back(mods, black, n, out[s0:s0 + n], packed, geom, bufs, kernel_events)
-                ev_back[i].record(main)
-        finally:
-            lib.mrinr_set_synthesis_clusters(packed.handle, 0)
+        for s0 in range(0, N, cs):
+            n = min(cs, N - s0)
+            self._chunk(images[s0:s0 + n], out[s0:s0 + n], packed, geom, bufs, skip_black, kernel_events)
         return out
 
     @torch.no_grad()

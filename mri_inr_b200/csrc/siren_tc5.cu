@@ -133,9 +133,10 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
 // Morlet envelope exp(-x^2/2) of two activations of group g (0..3) of a 16-activation chunk.  The special-function unit
 // (one MUFU.SIN per activation already) and the FMA pipe are both close to their limits in the Morlet epilogue, so the
 // envelope is split between them: groups whose bit is set in kMorletFmaMask use the FMA-pipe evaluation (gauss2),
-// the others ex2.approx on the special-function unit.  Measured (profiles/r02_morlet_variants.txt).
+// the others ex2.approx on the special-function unit.  Measured, sustained TFLOP/s of the kernel on dense modulations
+// (profiles/r02_morlet_variants.txt): all MUFU (round 1) 792, all FMA 773, groups 0 and 2 on the FMA pipe 820.
 #ifndef MRINR_MORLET_FMA_MASK
-#define MRINR_MORLET_FMA_MASK 0xF
+#define MRINR_MORLET_FMA_MASK 0x5
 #endif
 constexpr int kMorletFmaMask = MRINR_MORLET_FMA_MASK;
 __device__ __forceinline__ uint64_t morlet_env2(int g, float x0, float x1) {
@@ -298,9 +299,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float x = __uint_as_float(v[g * 4 + i]);
-          // X3 is the accuracy mode and waits for the tensor core anyway: full-precision sine there (sin.approx's 2^-21
-          // absolute error, amplified by large weights, was the mode's error floor: 6e-4 at W x 3)
-          s[g * 4 + i] = X3 ? sin_accurate(W0ONE ? x : P.w0 * x) : vsin_live(W0ONE ? x : P.w0 * x, mg[i]);
+          // (X3 too: a full-precision sine was measured there -- same error, the 22-bit operand split is the mode's
+          // floor, not sin.approx -- and cost 23 % of its throughput: profiles/r02_precision_table.txt)
+          s[g * 4 + i] = vsin_live(W0ONE ? x : P.w0 * x, mg[i]);
         }
         if (g > 0) finish_group(g - 1);
       }
@@ -352,14 +353,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         for (int g = 0; g < 4; ++g) {
           const float x0 = __uint_as_float(v[g * 4 + 0]), x1 = __uint_as_float(v[g * 4 + 1]);
           const float x2 = __uint_as_float(v[g * 4 + 2]), x3 = __uint_as_float(v[g * 4 + 3]);
-          float h0, h1, h2, h3;
-          if (X3) {
-            h0 = sin_accurate(W0ONE ? x0 : P.w0 * x0); h1 = sin_accurate(W0ONE ? x1 : P.w0 * x1);
-            h2 = sin_accurate(W0ONE ? x2 : P.w0 * x2); h3 = sin_accurate(W0ONE ? x3 : P.w0 * x3);
-          } else {
-            h0 = vsin_live(W0ONE ? x0 : P.w0 * x0, mw[g].x); h1 = vsin_live(W0ONE ? x1 : P.w0 * x1, mw[g].y);
-            h2 = vsin_live(W0ONE ? x2 : P.w0 * x2, mw[g].z); h3 = vsin_live(W0ONE ? x3 : P.w0 * x3, mw[g].w);
-          }
+          const float h0 = vsin_live(W0ONE ? x0 : P.w0 * x0, mw[g].x), h1 = vsin_live(W0ONE ? x1 : P.w0 * x1, mw[g].y);
+          const float h2 = vsin_live(W0ONE ? x2 : P.w0 * x2, mw[g].z), h3 = vsin_live(W0ONE ? x3 : P.w0 * x3, mw[g].w);
           if (ACT == MRINR_ACT_SINE) {
             d0 = fmaf(h0, mw[g].x, d0);
             d1 = fmaf(h1, mw[g].y, d1);

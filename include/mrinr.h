@@ -104,6 +104,11 @@ MRINR_API void mrinr_free_packed(MrinrPacked* p);
 /* Copies the layer-0 table [C,H] fp32 to d_out (test/introspection hook). */
 MRINR_API int  mrinr_packed_layer0_table(const MrinrPacked* p, float* d_out, void* stream);
 
+/* Re-derive every operand copy of an existing handle from NEW parameter values of the SAME configuration (same
+ * dimensions, activation, w0, precision, encoder present or not): no allocation, no synchronisation, all work on
+ * `stream`.  What a training loop calls after every optimizer step instead of free + pack. */
+MRINR_API int mrinr_refresh_weights(MrinrPacked* p, const MrinrWeightsView* weights, void* stream);
+
 /* The persistent synthesis kernel launches one CTA pair per SM pair (74 on a B200).  `clusters` > 0 caps that number,
  * leaving SMs free for kernels of another stream (the front end of the next chunk); 0 restores the default. */
 MRINR_API int mrinr_set_synthesis_clusters(MrinrPacked* p, int32_t clusters);

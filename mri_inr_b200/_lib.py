@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "mrinr_fft2c_workspace_bytes", "mrinr_fft2c", "mrinr_kspace_to_image",
     "mrinr_peer_alloc", "mrinr_peer_open", "mrinr_peer_close", "mrinr_peer_free",
     "mrinr_train_workspace_bytes", "mrinr_train_forward", "mrinr_train_backward",
-    "mrinr_set_synthesis_clusters",
+    "mrinr_set_synthesis_clusters", "mrinr_refresh_weights",
 )
 
 
@@ -116,6 +116,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mrinr_peer_close.argtypes = [c_void_p]
     lib.mrinr_peer_free.restype = c_int
     lib.mrinr_peer_free.argtypes = [c_void_p]
+    lib.mrinr_refresh_weights.restype = c_int
+    lib.mrinr_refresh_weights.argtypes = [c_void_p, POINTER(WeightsView), c_void_p]
     lib.mrinr_set_synthesis_clusters.restype = c_int
     lib.mrinr_set_synthesis_clusters.argtypes = [c_void_p, c_int32]
     lib.mrinr_train_workspace_bytes.restype = c_int64

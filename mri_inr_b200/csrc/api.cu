@@ -83,6 +83,108 @@ extern "C" void mrinr_free_packed(MrinrPacked* p) {
   delete p;
 }
 
+static bool view_has_encoder(const MrinrWeightsView* v) {
+  return v->d_enc_conv1_weight && v->d_enc_conv1_bias && v->d_enc_conv2_weight && v->d_enc_conv2_bias &&
+         v->d_enc_conv3_weight && v->d_enc_conv3_bias && v->d_enc_fc_weight && v->d_enc_fc_bias;
+}
+static bool view_has_any_encoder(const MrinrWeightsView* v) {
+  return v->d_enc_conv1_weight || v->d_enc_conv1_bias || v->d_enc_conv2_weight || v->d_enc_conv2_bias ||
+         v->d_enc_conv3_weight || v->d_enc_conv3_bias || v->d_enc_fc_weight || v->d_enc_fc_bias;
+}
+
+// Everything derived from the parameter VALUES: re-tiled / split operand copies, the layer-0 table, bias copies.
+// Writes into the buffers of an allocated MrinrPacked, all on `st`, no allocation and no synchronisation -- so that a
+// training loop can refresh the handle after every optimizer step (mrinr_refresh_weights) instead of rebuilding it.
+static int fill_packed(MrinrPacked* p, const MrinrWeightsView* v, cudaStream_t st) {
+  const int H = p->H, L = p->L, Z = p->Z, C = p->C, precision = p->precision;
+  const size_t w16q_layer = (size_t)2 * (H / 8 + 2) * (H / 2) * 8;     // elements per layer: [2 ranks][H/8+2][H/2][8]
+  int rc = 0;
+#define PK_RC(expr)             \
+  do {                          \
+    rc = (expr);                \
+    if (rc != 0) return rc;     \
+  } while (0)
+  MRINR_CUDA(cudaMemsetAsync(p->d_net_bias, 0, (size_t)L * H * sizeof(float), st));
+  MRINR_CUDA(cudaMemsetAsync(p->d_last_b, 0, sizeof(float), st));
+  const float* b0 = (v->d_net_bias && v->d_net_bias[0]) ? v->d_net_bias[0] : nullptr;
+  // layer-0 parameters as three [H] rows: W_0[:,0], W_0[:,1], b_0
+  MRINR_CUDA(cudaMemsetAsync(p->d_layer0, 0, (size_t)3 * H * sizeof(float), st));
+  MRINR_CUDA(cudaMemcpy2DAsync(p->d_layer0, sizeof(float), v->d_net_weight[0], 2 * sizeof(float), sizeof(float), H,
+                               cudaMemcpyDeviceToDevice, st));
+  MRINR_CUDA(cudaMemcpy2DAsync(p->d_layer0 + H, sizeof(float), v->d_net_weight[0] + 1, 2 * sizeof(float), sizeof(float), H,
+                               cudaMemcpyDeviceToDevice, st));
+  if (b0) MRINR_CUDA(cudaMemcpyAsync(p->d_layer0 + 2 * H, b0, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  MRINR_CUDA(cudaMemcpyAsync(p->d_grid, v->d_grid, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  PK_RC(run_layer0_table(v->d_grid, v->d_net_weight[0], b0, C, H, p->w0_initial, p->activation, p->d_table0, st));
+#ifdef MRINR_LAB
+  PK_RC(run_table16(p->d_table0, (long long)C * H, precision == MRINR_PREC_BF16, p->d_table16, st));
+#endif
+  for (int l = 0; l < L; ++l) {
+    if (v->d_net_bias && v->d_net_bias[l])
+      MRINR_CUDA(cudaMemcpyAsync(p->d_net_bias + (size_t)l * H, v->d_net_bias[l], H * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+    MRINR_CUDA(cudaMemcpyAsync(p->d_mod_bias + (size_t)l * H, v->d_mod_bias[l], H * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  for (int l = 1; l < L; ++l) {
+    PK_RC(run_transpose(v->d_net_weight[l], H, H, p->d_net_wT + (size_t)(l - 1) * H * H, st));
+    if (precision != MRINR_PREC_FP32) {
+#ifdef MRINR_LAB
+      PK_RC(run_pack_w16(v->d_net_weight[l], H, precision == MRINR_PREC_BF16, p->d_net_w16 + (size_t)(l - 1) * H * H, st));
+      PK_RC(run_pack_w16_pair(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
+                              p->d_net_w16p + (size_t)(l - 1) * H * H, st));
+#endif
+      const float* bl = v->d_net_bias ? v->d_net_bias[l] : nullptr;
+      if (precision == MRINR_PREC_FP16X3) {
+        for (int part = 0; part < 2; ++part)
+          PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], bl, H, 0,
+                                       p->d_net_w16x3 + ((size_t)(l - 1) * 2 + part) * w16q_layer, st, part));
+      } else {
+        PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], bl, H, precision == MRINR_PREC_BF16,
+                                     p->d_net_w16q + (size_t)(l - 1) * w16q_layer, st));
+      }
+    }
+  }
+  MRINR_CUDA(cudaMemcpyAsync(p->d_last_w, v->d_last_weight, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (v->d_last_bias)
+    MRINR_CUDA(cudaMemcpyAsync(p->d_last_b, v->d_last_bias, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // modulator: layer 0 is [H,Z]; layers >= 1 are [H, H+Z] with the hidden columns first
+  float* dst = p->d_mod_wT;
+  PK_RC(run_transpose(v->d_mod_weight[0], H, Z, dst, st));
+  dst += (size_t)Z * H;
+  for (int l = 1; l < L; ++l) {
+    PK_RC(run_transpose(v->d_mod_weight[l], H, H + Z, dst, st));
+    dst += (size_t)(H + Z) * H;
+  }
+  if (p->mod_tc) {      // modulator on the tensor cores: split-fp16 operands per layer (dense_tc.cu)
+    for (int l = 0; l < L; ++l)
+      PK_RC(run_pack_split(v->d_mod_weight[l], H, l == 0 ? Z : H + Z, p->d_mod_ws + p->mod_ws_off[l], st));
+  }
+  if (p->has_encoder) {
+    MRINR_CUDA(cudaMemcpyAsync(p->d_enc_c1w, v->d_enc_conv1_weight, 16 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MRINR_CUDA(cudaMemcpyAsync(p->d_enc_c1b, v->d_enc_conv1_bias, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MRINR_CUDA(cudaMemcpyAsync(p->d_enc_c2w, v->d_enc_conv2_weight, 32 * 16 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MRINR_CUDA(cudaMemcpyAsync(p->d_enc_c2b, v->d_enc_conv2_bias, 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MRINR_CUDA(cudaMemcpyAsync(p->d_enc_b3, v->d_enc_conv3_bias, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MRINR_CUDA(cudaMemcpyAsync(p->d_enc_bf, v->d_enc_fc_bias, (size_t)Z * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PK_RC(run_pack_split(v->d_enc_conv3_weight, 64, 2048, p->d_enc_w3s, st));
+    PK_RC(run_pack_split(v->d_enc_fc_weight, Z, 64, p->d_enc_wfs, st));
+  }
+#undef PK_RC
+  return 0;
+}
+
+static int check_view_pointers(const MrinrWeightsView* v, const char* who) {
+  MRINR_REQUIRE(v->d_grid && v->d_net_weight && v->d_last_weight && v->d_mod_weight && v->d_mod_bias, MRINR_E_ARG,
+                "%s: null weight pointer", who);
+  for (int l = 0; l < v->num_layers; ++l)
+    MRINR_REQUIRE(v->d_net_weight[l] && v->d_mod_weight[l] && v->d_mod_bias[l], MRINR_E_ARG,
+                  "%s: null pointer for layer %d", who, l);
+  if (view_has_any_encoder(v))
+    MRINR_REQUIRE(view_has_encoder(v), MRINR_E_ARG, "%s: the encoder needs all eight tensors (or none)", who);
+  return 0;
+}
+
 extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void* stream, MrinrPacked** out) {
   MRINR_REQUIRE(v && out, MRINR_E_ARG, "mrinr_pack_weights: null argument");
   *out = nullptr;
@@ -111,11 +213,12 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
                   "mrinr_pack_weights: the tensor-core path requires siren_patch_size^2 >= 128 (got %d)",
                   v->siren_patch_size);
   }
-  MRINR_REQUIRE(v->d_grid && v->d_net_weight && v->d_last_weight && v->d_mod_weight && v->d_mod_bias, MRINR_E_ARG,
-                "mrinr_pack_weights: null weight pointer");
-  for (int l = 0; l < v->num_layers; ++l)
-    MRINR_REQUIRE(v->d_net_weight[l] && v->d_mod_weight[l] && v->d_mod_bias[l], MRINR_E_ARG,
-                  "mrinr_pack_weights: null pointer for layer %d", l);
+  int rc = check_view_pointers(v, "mrinr_pack_weights");
+  if (rc != 0) return rc;
+  if (view_has_any_encoder(v))
+    MRINR_REQUIRE(v->outer_patch_size == 32 && dense_split_supported(v->latent_dim, 64, 0), MRINR_E_UNSUPPORTED,
+                  "mrinr_pack_weights: the encoder is hard-wired to 32x32 patches (siren_encoder.py:498-512) and needs "
+                  "latent_dim in {64,128,256} (got O=%d Z=%d)", v->outer_patch_size, v->latent_dim);
 
   int dev = 0;
   MRINR_CUDA(cudaGetDevice(&dev));
@@ -134,7 +237,6 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
   p->device = dev; p->num_sms = prop.multiProcessorCount;
   const int H = p->H, L = p->L, Z = p->Z, C = p->C;
 
-  int rc = 0;
 #define PK_CUDA(expr)                                                                         \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -144,14 +246,11 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
       goto fail;                                                                              \
     }                                                                                         \
   } while (0)
-#define PK_RC(expr)          \
-  do {                       \
-    rc = (expr);             \
-    if (rc != 0) goto fail;  \
-  } while (0)
 
   {
+    // ---- allocation (sizes depend on the configuration only) ...
     const size_t mod_w_elems = (size_t)Z * H + (size_t)(L - 1) * (H + Z) * H;
+    const size_t w16q_layer = (size_t)2 * (H / 8 + 2) * (H / 2) * 8;
     PK_CUDA(cudaMalloc(&p->d_table0, (size_t)C * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_net_wT, (size_t)(L - 1) * H * H * sizeof(float)));
 #ifdef MRINR_LAB   // operand copies of the retired kernel variants (lab/): not part of the product library
@@ -159,7 +258,6 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     PK_CUDA(cudaMalloc(&p->d_net_w16, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
     PK_CUDA(cudaMalloc(&p->d_net_w16p, (size_t)(L - 1) * H * H * sizeof(uint16_t)));
 #endif
-    const size_t w16q_layer = (size_t)2 * (H / 8 + 2) * (H / 2) * 8;     // elements per layer: [2 ranks][H/8+2][H/2][8]
     if (precision == MRINR_PREC_FP16 || precision == MRINR_PREC_BF16)
       PK_CUDA(cudaMalloc(&p->d_net_w16q, (size_t)(L - 1) * w16q_layer * sizeof(uint16_t)));
     if (precision == MRINR_PREC_FP16X3)
@@ -173,88 +271,17 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
     PK_CUDA(cudaMalloc(&p->d_mod_bias, (size_t)L * H * sizeof(float)));
     PK_CUDA(cudaMalloc(&p->d_errflag, sizeof(int32_t)));
     PK_CUDA(cudaMemsetAsync(p->d_errflag, 0, sizeof(int32_t), st));
-    PK_CUDA(cudaMemsetAsync(p->d_net_bias, 0, (size_t)L * H * sizeof(float), st));
-    PK_CUDA(cudaMemsetAsync(p->d_last_b, 0, sizeof(float), st));
-
-    const float* b0 = (v->d_net_bias && v->d_net_bias[0]) ? v->d_net_bias[0] : nullptr;
-    // layer-0 parameters as three [H] rows: W_0[:,0], W_0[:,1], b_0
-    PK_CUDA(cudaMemsetAsync(p->d_layer0, 0, (size_t)3 * H * sizeof(float), st));
-    PK_CUDA(cudaMemcpy2DAsync(p->d_layer0, sizeof(float), v->d_net_weight[0], 2 * sizeof(float), sizeof(float), H,
-                              cudaMemcpyDeviceToDevice, st));
-    PK_CUDA(cudaMemcpy2DAsync(p->d_layer0 + H, sizeof(float), v->d_net_weight[0] + 1, 2 * sizeof(float), sizeof(float), H,
-                              cudaMemcpyDeviceToDevice, st));
-    if (b0) PK_CUDA(cudaMemcpyAsync(p->d_layer0 + 2 * H, b0, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    PK_CUDA(cudaMemcpyAsync(p->d_grid, v->d_grid, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    PK_RC(run_layer0_table(v->d_grid, v->d_net_weight[0], b0, C, H, p->w0_initial, p->activation, p->d_table0, st));
-#ifdef MRINR_LAB
-    PK_RC(run_table16(p->d_table0, (long long)C * H, precision == MRINR_PREC_BF16, p->d_table16, st));
-#endif
-    for (int l = 0; l < L; ++l) {
-      if (v->d_net_bias && v->d_net_bias[l])
-        PK_CUDA(cudaMemcpyAsync(p->d_net_bias + (size_t)l * H, v->d_net_bias[l], H * sizeof(float),
-                                cudaMemcpyDeviceToDevice, st));
-      PK_CUDA(cudaMemcpyAsync(p->d_mod_bias + (size_t)l * H, v->d_mod_bias[l], H * sizeof(float),
-                              cudaMemcpyDeviceToDevice, st));
-    }
-    for (int l = 1; l < L; ++l) {
-      PK_RC(run_transpose(v->d_net_weight[l], H, H, p->d_net_wT + (size_t)(l - 1) * H * H, st));
-      if (precision != MRINR_PREC_FP32) {
-#ifdef MRINR_LAB
-        PK_RC(run_pack_w16(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
-                           p->d_net_w16 + (size_t)(l - 1) * H * H, st));
-        PK_RC(run_pack_w16_pair(v->d_net_weight[l], H, precision == MRINR_PREC_BF16,
-                                p->d_net_w16p + (size_t)(l - 1) * H * H, st));
-#endif
-        const float* bl = v->d_net_bias ? v->d_net_bias[l] : nullptr;
-        if (precision == MRINR_PREC_FP16X3) {
-          for (int part = 0; part < 2; ++part)
-            PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], bl, H, 0,
-                                         p->d_net_w16x3 + ((size_t)(l - 1) * 2 + part) * w16q_layer, st, part));
-        } else {
-          PK_RC(run_pack_w16_pair_bias(v->d_net_weight[l], bl, H, precision == MRINR_PREC_BF16,
-                                       p->d_net_w16q + (size_t)(l - 1) * w16q_layer, st));
-        }
-      }
-    }
-    PK_CUDA(cudaMemcpyAsync(p->d_last_w, v->d_last_weight, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (v->d_last_bias)
-      PK_CUDA(cudaMemcpyAsync(p->d_last_b, v->d_last_bias, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    // modulator: layer 0 is [H,Z]; layers >= 1 are [H, H+Z] with the hidden columns first
-    float* dst = p->d_mod_wT;
-    PK_RC(run_transpose(v->d_mod_weight[0], H, Z, dst, st));
-    dst += (size_t)Z * H;
-    for (int l = 1; l < L; ++l) {
-      PK_RC(run_transpose(v->d_mod_weight[l], H, H + Z, dst, st));
-      dst += (size_t)(H + Z) * H;
-    }
     // modulator on the tensor cores: split-fp16 operands per layer (dense_tc.cu)
     p->mod_tc = (precision != MRINR_PREC_FP32) && dense_split_supported(H, Z, 0) && dense_split_supported(H, H, Z);
     if (p->mod_tc) {
       PK_CUDA(cudaMalloc(&p->d_mod_ws, mod_w_elems * 2 * sizeof(uint16_t)));
       size_t off = 0;
       for (int l = 0; l < L; ++l) {
-        const int K = l == 0 ? Z : H + Z;
         p->mod_ws_off[l] = off;
-        PK_RC(run_pack_split(v->d_mod_weight[l], H, K, p->d_mod_ws + off, st));
-        off += (size_t)2 * H * K;
+        off += (size_t)2 * H * (l == 0 ? Z : H + Z);
       }
     }
-    // patch encoder (optional)
-    const bool any_enc = v->d_enc_conv1_weight || v->d_enc_conv1_bias || v->d_enc_conv2_weight || v->d_enc_conv2_bias ||
-                         v->d_enc_conv3_weight || v->d_enc_conv3_bias || v->d_enc_fc_weight || v->d_enc_fc_bias;
-    if (any_enc) {
-      if (!(v->d_enc_conv1_weight && v->d_enc_conv1_bias && v->d_enc_conv2_weight && v->d_enc_conv2_bias &&
-            v->d_enc_conv3_weight && v->d_enc_conv3_bias && v->d_enc_fc_weight && v->d_enc_fc_bias)) {
-        set_error("mrinr_pack_weights: the encoder needs all eight tensors (or none)");
-        rc = MRINR_E_ARG;
-        goto fail;
-      }
-      if (v->outer_patch_size != 32 || !dense_split_supported(Z, 64, 0)) {
-        set_error("mrinr_pack_weights: the encoder is hard-wired to 32x32 patches (siren_encoder.py:498-512) and needs "
-                  "latent_dim in {64,128,256} (got O=%d Z=%d)", v->outer_patch_size, Z);
-        rc = MRINR_E_UNSUPPORTED;
-        goto fail;
-      }
+    if (view_has_encoder(v)) {      // patch encoder (optional)
       PK_CUDA(cudaMalloc(&p->d_enc_c1w, 16 * 9 * sizeof(float)));
       PK_CUDA(cudaMalloc(&p->d_enc_c1b, 16 * sizeof(float)));
       PK_CUDA(cudaMalloc(&p->d_enc_c2w, 32 * 16 * 9 * sizeof(float)));
@@ -263,16 +290,11 @@ extern "C" int mrinr_pack_weights(const MrinrWeightsView* v, int precision, void
       PK_CUDA(cudaMalloc(&p->d_enc_b3, 64 * sizeof(float)));
       PK_CUDA(cudaMalloc(&p->d_enc_wfs, (size_t)2 * Z * 64 * sizeof(uint16_t)));
       PK_CUDA(cudaMalloc(&p->d_enc_bf, (size_t)Z * sizeof(float)));
-      PK_CUDA(cudaMemcpyAsync(p->d_enc_c1w, v->d_enc_conv1_weight, 16 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      PK_CUDA(cudaMemcpyAsync(p->d_enc_c1b, v->d_enc_conv1_bias, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      PK_CUDA(cudaMemcpyAsync(p->d_enc_c2w, v->d_enc_conv2_weight, 32 * 16 * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      PK_CUDA(cudaMemcpyAsync(p->d_enc_c2b, v->d_enc_conv2_bias, 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      PK_CUDA(cudaMemcpyAsync(p->d_enc_b3, v->d_enc_conv3_bias, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      PK_CUDA(cudaMemcpyAsync(p->d_enc_bf, v->d_enc_fc_bias, (size_t)Z * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      PK_RC(run_pack_split(v->d_enc_conv3_weight, 64, 2048, p->d_enc_w3s, st));
-      PK_RC(run_pack_split(v->d_enc_fc_weight, Z, 64, p->d_enc_wfs, st));
       p->has_encoder = 1;
     }
+    // ---- ... then everything derived from the values
+    rc = fill_packed(p, v, st);
+    if (rc != 0) goto fail;
     PK_CUDA(cudaStreamSynchronize(st));
   }
   *out = p;
@@ -281,7 +303,17 @@ fail:
   mrinr_free_packed(p);
   return rc;
 #undef PK_CUDA
-#undef PK_RC
+}
+
+extern "C" int mrinr_refresh_weights(MrinrPacked* p, const MrinrWeightsView* v, void* stream) {
+  MRINR_REQUIRE(p && v, MRINR_E_ARG, "mrinr_refresh_weights: null argument");
+  MRINR_REQUIRE(v->dim_in == 2 && v->dim_out == 1 && v->dim_hidden == p->H && v->num_layers == p->L &&
+                    v->latent_dim == p->Z && v->siren_patch_size == p->S && v->activation == p->activation &&
+                    v->w0 == p->w0 && v->w0_initial == p->w0_initial && (view_has_encoder(v) ? 1 : 0) == p->has_encoder,
+                MRINR_E_ARG, "mrinr_refresh_weights: the view does not have the configuration the handle was packed for");
+  const int rc = check_view_pointers(v, "mrinr_refresh_weights");
+  if (rc != 0) return rc;
+  return fill_packed(p, v, (cudaStream_t)stream);
 }
 
 extern "C" int mrinr_set_synthesis_clusters(MrinrPacked* p, int32_t clusters) {

@@ -279,8 +279,8 @@ class ModulatedSiren(nn.Module):
     def _packed(self) -> ops.PackedWeights:
         return self._packed_as(self._effective_precision())
 
-    def _build_pack(self, precision: str) -> ops.PackedWeights:
-        return ops.PackedWeights(
+    def _pack_kwargs(self):
+        return dict(
             grid=self.grid,
             net_weights=[l.weight for l in self.net.layers],
             net_biases=[l.bias for l in self.net.layers],
@@ -288,9 +288,11 @@ class ModulatedSiren(nn.Module):
             mod_weights=[s[0].weight for s in self.modulator.layers],
             mod_biases=[s[0].bias for s in self.modulator.layers],
             w0=self.net.w0, w0_initial=self.net.w0_initial, activation=self.activation,
-            precision=precision, siren_patch_size=self.siren_patch_size,
-            encoder_params=self.encoder.params(),
+            siren_patch_size=self.siren_patch_size, encoder_params=self.encoder.params(),
             outer_patch_size=self.outer_patch_size)
+
+    def _build_pack(self, precision: str) -> ops.PackedWeights:
+        return ops.PackedWeights(precision=precision, **self._pack_kwargs())
 
     def _resolve_auto(self, mods: torch.Tensor) -> None:
         """One-off self-check of ``precision="auto"``: evaluate a strided sample of the batch's modulations in every
@@ -324,9 +326,13 @@ class ModulatedSiren(nn.Module):
             if not self.grid.is_cuda:
                 raise RuntimeError("mri_inr_b200.ModulatedSiren runs on CUDA only: call .to('cuda') first "
                                    "(there is no CPU fallback)")
-            if self._pack is not None:
-                self._pack.free()
-            self._pack = self._build_pack(precision)
+            # the same configuration with new VALUES (an optimizer step, load_state_dict): refresh the existing handle
+            # in place -- no allocation, no synchronisation; anything else (precision, shapes, device): a new handle
+            if not (self._pack is not None and self._pack.precision == precision
+                    and self._pack.refresh(**self._pack_kwargs())):
+                if self._pack is not None:
+                    self._pack.free()
+                self._pack = self._build_pack(precision)
             self._pack_key = key
         return self._pack
 

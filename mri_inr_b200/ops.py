@@ -133,6 +133,36 @@ class PackedWeights:
         self.C = siren_patch_size * siren_patch_size
         self.precision = precision
         self.activation = activation
+        # what a refresh must leave unchanged (everything that sizes or specialises the packed buffers)
+        self.signature = self._signature(grid, net_weights, mod_weights, w0, w0_initial, activation, siren_patch_size,
+                                         encoder_params, net_biases, last_bias)
+
+    @staticmethod
+    def _signature(grid, net_weights, mod_weights, w0, w0_initial, activation, siren_patch_size, encoder_params,
+                   net_biases, last_bias):
+        return (str(grid.device), len(net_weights), tuple(net_weights[0].shape), tuple(mod_weights[0].shape),
+                float(w0), float(w0_initial), activation if activation in _lib.ACTIVATIONS else "sine",
+                int(siren_patch_size), encoder_params is not None, tuple(b is not None for b in net_biases),
+                last_bias is not None)
+
+    def refresh(self, *, grid, net_weights, net_biases, last_weight, last_bias, mod_weights, mod_biases, w0, w0_initial,
+                activation, siren_patch_size, encoder_params=None, outer_patch_size: int = 32) -> bool:
+        """Re-derive the packed copies from new parameter VALUES (``mrinr_refresh_weights``: no allocation, no
+        synchronisation; on the current stream).  Returns ``False`` -- and does nothing -- when the configuration
+        differs from the one this handle was packed for (the caller then builds a new handle)."""
+        sig = self._signature(grid, net_weights, mod_weights, w0, w0_initial, activation, siren_patch_size,
+                              encoder_params, net_biases, last_bias)
+        if self._handle is None or sig != self.signature:
+            return False
+        view, keep = weights_view(grid=grid, net_weights=net_weights, net_biases=net_biases, last_weight=last_weight,
+                                  last_bias=last_bias, mod_weights=mod_weights, mod_biases=mod_biases, w0=w0,
+                                  w0_initial=w0_initial, activation=activation, siren_patch_size=siren_patch_size,
+                                  encoder_params=encoder_params, outer_patch_size=outer_patch_size)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mrinr_refresh_weights(self.handle, ctypes.byref(view), _lib.stream_ptr(self.device)),
+                       "refresh_weights")
+        del keep
+        return True
 
     @property
     def handle(self) -> c_void_p:

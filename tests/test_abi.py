@@ -28,7 +28,7 @@ def test_header_declares_expected_symbols():
     from mri_inr_b200 import _lib
 
     assert header_symbols() == sorted(_lib.EXPORTED_SYMBOLS)
-    assert len(header_symbols()) == 30
+    assert len(header_symbols()) == 31
 
 
 def test_library_exports_every_declared_symbol(lib):

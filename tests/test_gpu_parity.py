@@ -803,3 +803,36 @@ def test_image_metrics_match_direct_window_formulation(hw):
         want = ometrics.ssim_direct(full[i], pred[i])
         print(f"{hw} pair {i}: ssim {got[i, 1]:.9f} direct {want:.9f}")
         assert abs(got[i, 1] - want) <= 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-3), ("fp16x3", 1e-5), ("fp32", 2e-5)])
+def test_new_parameter_values_refresh_the_packed_handle_in_place(precision, tol):
+    """mrinr_refresh_weights: after load_state_dict / an in-place parameter update the SAME MrinrPacked handle is
+    re-filled (no allocation, no synchronisation) and the forward follows the new values; a different configuration
+    (precision) still builds a new handle."""
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, precision)
+    tiles_np = synth_tiles(17, 9)
+    tiles = torch.from_numpy(tiles_np).to(DEV)
+    with torch.no_grad():
+        m(tiles)
+    pack = m._pack
+    handle = pack.handle.value
+    sd2 = osiren.synth_state_dict(seed=77, mod_bias_shift=0.4)
+    m.load_state_dict(sd2, strict=True)
+    with torch.no_grad():
+        y = m(tiles).cpu().numpy()
+    assert m._pack is pack and pack.handle.value == handle          # refreshed in place
+    want = osiren.model_forward(sd2, torch.from_numpy(tiles_np), activation=act).numpy()
+    assert np.abs(y - want).max() <= tol
+    with torch.no_grad():
+        m.net.layers[1].bias.add_(0.05)                             # in-place update: version counter changes
+        y2 = m(tiles).cpu().numpy()
+    sd3 = {k: v.clone() for k, v in sd2.items()}
+    sd3["net.layers.1.bias"] = sd3["net.layers.1.bias"] + 0.05
+    assert m._pack is pack
+    assert np.abs(y2 - osiren.model_forward(sd3, torch.from_numpy(tiles_np), activation=act).numpy()).max() <= tol
+    m.precision = "fp32" if precision != "fp32" else "fp16"
+    with torch.no_grad():
+        m(tiles)
+    assert m._pack is not pack                                      # another precision: a new handle

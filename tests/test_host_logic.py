@@ -197,3 +197,31 @@ def test_fma_pipe_gaussian_coefficients():
     near = np.abs(x) < 9
     assert np.abs(g[near] / ref[near] - 1).max() <= 1e-5
     assert np.all(np.isfinite(g)) and np.all(g >= 0) and g[np.abs(x) > 13.5].max() < 1e-37
+
+
+def test_bench_chunking_and_reference_arm_line():
+    """bench.py host logic: the chunk size divides every rank's block without a ragged tail worth mentioning, and the
+    `--impl reference` arm prints one JSON line with the contract's keys (CPU only, bounded sample)."""
+    import json
+    import subprocess
+    import sys
+
+    import bench
+    from mri_inr_b200.dist import shard_range
+
+    for world in (1, 2, 4, 8):
+        n_local = shard_range(10340, 0, world)[1]
+        c = bench.auto_chunk(n_local)
+        n_chunks = -(-n_local // c)
+        assert 200 <= c <= 235 and n_chunks * c - n_local < n_chunks          # last chunk short by < 1 slice per chunk
+    assert bench.auto_chunk(0) == 235 and bench.auto_chunk(7) == 7
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-slices", "1",
+                        "--num-layers", "3"], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["num_layers"] == 3
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1

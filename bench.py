@@ -201,40 +201,71 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _shared_cudart():
+    """ctypes handle of the libcudart PyTorch itself uses (already loaded in this process): needed to read and CLEAR
+    the runtime's last-error slot, which torch's own cudart binding does not expose."""
+    import ctypes
+
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libcudart" in line:
+                    return ctypes.CDLL(line.split()[-1])
+    except OSError:
+        pass
+    return None
+
+
 class SharedHostBuffer:
-    """ONE result buffer in POSIX shared memory that every rank maps and page-locks, so each rank streams its block
+    """ONE result buffer in POSIX shared memory that every rank maps, so each rank streams its block
     host -> device -> host over its own PCIe link (funnelling 4.2 GB through rank 0's link would serialise the
-    downloads).  Construction and ``close()`` are collective; if any rank fails, every rank ends up with ``ok == False``
-    (the callers then fall back to gather + one download on rank 0) and the collective sequence stays aligned."""
+    downloads).  Every rank page-locks ONLY ITS OWN block of the buffer, after touching it (round 1 registered the
+    whole buffer on every rank before the pages existed: N processes faulting in and pinning the same untouched tmpfs
+    pages at the same time made cudaHostRegister fail with cudaErrorOperatingSystem now and then, and the stale error
+    it left in the CUDA runtime killed the next launch of the rank -- the rc = 1 of SCALE_r01's N = 4 point).
+    Construction and ``close()`` are collective; if any rank fails, every rank ends up with ``ok == False`` (the callers
+    then fall back to gather + one download on rank 0) and the collective sequence stays aligned."""
 
     def __init__(self, n_total, img, rank, world, dev, s0, s1):
+        import ctypes
+
         import torch
         import torch.distributed as dist
 
-        self.rank, self.tensor, self._registered = rank, None, False
+        self.rank, self.tensor, self._registered = rank, None, None
         self.path = f"/dev/shm/mrinr_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}.bin"
         nbytes = n_total * img * img * 4
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        failed = 0
         if rank == 0:
             try:
                 with open(self.path, "wb") as f:
                     f.truncate(nbytes)
             except Exception as e:                  # noqa: BLE001
-                flag += 1
+                failed = 1
                 print(f"[bench] rank {rank}: cannot create {self.path}: {e}", file=sys.stderr, flush=True)
+        flag = torch.tensor([failed], dtype=torch.int32, device=dev)
         dist.all_reduce(flag)                       # also the barrier behind which the file exists
+        failed = 0
         if int(flag.item()) == 0:
+            rt = _shared_cudart()
             try:
                 t = torch.from_file(self.path, shared=True, size=n_total * img * img, dtype=torch.float32)
-                rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
-                if int(rc) != 0:
-                    raise RuntimeError(f"cudaHostRegister returned {rc}")
-                self._registered = True
                 self.tensor = t.view(n_total, img, img)
-                self.tensor[s0:s1].zero_()          # touch my pages
+                mine = self.tensor[s0:s1]
+                mine.zero_()                        # my pages exist before they are pinned; nobody else touches them
+                if mine.numel() > 0:
+                    if rt is None:
+                        raise RuntimeError("libcudart not found in /proc/self/maps")
+                    rt.cudaHostRegister.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint]
+                    rc = rt.cudaHostRegister(ctypes.c_void_p(mine.data_ptr()), mine.numel() * 4, 0)
+                    if rc != 0:
+                        rt.cudaGetLastError()       # clear the runtime's last-error slot: the failure is handled HERE
+                        raise RuntimeError(f"cudaHostRegister failed with CUDA error {rc}")
+                    self._registered = (rt, mine.data_ptr())
             except Exception as e:                  # noqa: BLE001 - any failure selects the fallback on every rank
-                flag += 1
+                failed = 1
                 print(f"[bench] rank {rank}: shared host buffer unavailable ({e})", file=sys.stderr, flush=True)
+        flag = torch.tensor([failed + (1 if int(flag.item()) else 0)], dtype=torch.int32, device=dev)
         dist.all_reduce(flag)
         self.ok = int(flag.item()) == 0
         if not self.ok:
@@ -242,15 +273,19 @@ class SharedHostBuffer:
 
     def close(self, barrier=True):
         """Collective (one barrier) unless ``barrier=False`` (the caller has just synchronised the ranks itself)."""
+        import ctypes
+
         import torch
         import torch.distributed as dist
 
         if barrier:
             dist.barrier()                          # nobody writes into the buffer any more
-        if self.tensor is not None and self._registered:
+        if self._registered is not None:
+            rt, ptr = self._registered
             torch.cuda.synchronize()
-            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
-            self._registered = False
+            if rt.cudaHostUnregister(ctypes.c_void_p(ptr)) != 0:
+                rt.cudaGetLastError()
+            self._registered = None
         self.tensor = None
         if self.rank == 0:                          # unlinking while other ranks still map the file is fine on POSIX
             try:

@@ -538,7 +538,7 @@ def run_ours(args):
     # ---- teardown.  The measurement is complete and printed.  ONE barrier (every rank is done with the shared host
     # buffer and the peer-mapped device buffer), then only local clean-up: no collective runs after a mapping has been
     # closed (see PeerGather._release).  A failure here is reported on stderr but does not turn a finished measurement
-    # into rc != 0 (SCALE_r01's N=4 point died in this region on exactly the two ring neighbours of rank 0).
+    # into rc != 0.
     if world > 1:
         try:
             recon = None

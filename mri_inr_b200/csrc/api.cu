@@ -24,9 +24,10 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // Error codes that a kernel launch can never produce but that other components of the process leave behind in the
-// runtime's (non-sticky) last-error slot: peer access enabled twice (this library's lazy CUDA-IPC mapping and NCCL's
-// P2P transport both enable it towards rank 0's GPU -- on exactly the ring neighbours of rank 0), host memory
-// registered twice.  They are not ours to report: a stale one would turn the next launch into a spurious failure.
+// runtime's (non-sticky) last-error slot: peer access enabled twice (this library's lazy CUDA-IPC mapping and a
+// collective library's P2P transport may both enable it towards the same GPU), host memory registered twice.  They are
+// not ours to report: a stale one would turn the next launch into a spurious failure (that mechanism -- a handled
+// cudaHostRegister failure, then a launch check tripping over its stale code -- was the N=4 rc=1 of round 1's sweep).
 static bool benign_stale_error(cudaError_t e) {
   return e == cudaErrorPeerAccessAlreadyEnabled || e == cudaErrorPeerAccessNotEnabled ||
          e == cudaErrorHostMemoryAlreadyRegistered || e == cudaErrorHostMemoryNotRegistered;

@@ -177,10 +177,10 @@ class PeerGather:
 
     def _release(self, barrier: bool = True) -> None:
         """ONE barrier that every rank takes whatever its local state (nobody stores into the buffer any more), then
-        the purely local part: non-owners unmap, the owner frees.  No collective runs AFTER a mapping has been closed:
-        the peer access that the lazy CUDA-IPC mapping shares with NCCL's P2P transport (towards the owner's GPU, on the
-        owner's ring neighbours) must not be torn down underneath a collective.  The collective sequence is the same
-        on every rank even after a partial failure."""
+        the purely local part: non-owners unmap, the owner frees.  No collective runs AFTER a mapping has been closed
+        (the lazily enabled peer access of the CUDA-IPC mapping is state it shares with NCCL's P2P transport towards
+        the owner's GPU: nothing is torn down underneath a collective).  The collective sequence is the same on every
+        rank even after a partial failure."""
         errors = []
         self.full = self.local_view = None
         with self._device_ctx():

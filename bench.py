@@ -253,6 +253,8 @@ class SharedHostBuffer:
                 self.tensor = t.view(n_total, img, img)
                 mine = self.tensor[s0:s1]
                 mine.zero_()                        # my pages exist before they are pinned; nobody else touches them
+                if os.environ.get("MRINR_BENCH_FAIL_SHM") == "odd" and rank % 2 == 1:
+                    raise RuntimeError("failure injected by MRINR_BENCH_FAIL_SHM=odd (tests/test_gpu_multi.py)")
                 if mine.numel() > 0:
                     if rt is None:
                         raise RuntimeError("libcudart not found in /proc/self/maps")

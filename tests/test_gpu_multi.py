@@ -11,10 +11,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun_bench(n, port, extra):
+def _torchrun_bench(n, port, extra, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(port), "bench.py", "--gpus", str(n)] + extra
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -48,3 +49,16 @@ def test_bench_two_gpus_odd_chunk_count_and_ragged_blocks():
     assert line["n_gpus"] == 2 and line["config"]["chunk_slices"] == 167
     line = _torchrun_bench(2, 29661, ["--steps", "2", "--warmup", "3", "--slices", "1001", "--exchange", "nccl", "--no-burst"])
     assert "NCCL gather" in line["config"]["exchange"]
+
+
+@pytest.mark.gpu
+def test_bench_shared_host_buffer_failure_on_one_rank_selects_the_fallback():
+    """The mechanism behind SCALE_r01's N=4 rc=1: page-locking the shared host result buffer fails on SOME ranks.  Every
+    rank must then take the fallback of the e2e leg (gather on the device, one download on rank 0) and the run must
+    finish with rc 0 and a complete line."""
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    line = _torchrun_bench(2, 29670, ["--steps", "2", "--warmup", "3", "--slices", "517", "--no-burst"],
+                           env={"MRINR_BENCH_FAIL_SHM": "odd"})
+    assert line["n_gpus"] == 2 and line["e2e"]["value"] > 0
+    assert "gather to rank 0" in line["e2e"]["result"]

@@ -129,14 +129,18 @@ def test_optimizer_steps_reduce_the_loss():
     target = torch.from_numpy(synth_tiles(11, 16)).to(DEV)[:, 4:28, 4:28]      # learn to reproduce the centre crop
     losses = []
     torch.manual_seed(0)
+    criterion = torch.nn.MSELoss()                                        # training.py:108-114 ("MSE")
     for it in range(12):
-        opt.zero_grad()
-        out = m(under)
-        loss = torch.nn.functional.mse_loss(out, target)
-        scaler.scale(loss).backward()
-        scaler.step(opt)
-        scaler.update()
-        losses.append(float(loss.item()))
+        with torch.amp.autocast("cuda", enabled=True):                    # training.py:197-204, line for line
+            opt.zero_grad()
+            outputs = m(under)
+            loss = criterion(outputs, target)
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+            loss_item = loss.item()
+        assert outputs.dtype == torch.float32
+        losses.append(float(loss_item))
     print("losses", [round(x, 5) for x in losses])
     assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0]
 

@@ -7,7 +7,7 @@ echo "== full GPU suite (as the driver runs it)"; timeout 1200 python -m pytest 
 echo "== morlet variants"
 rm -f $O/e_morlet.txt
 timeout 120 python tools/morlet_bench.py >> $O/e_morlet.txt 2>&1
-for m in 0x0 0xA 0xF 0x5_g1 0x5_g2 0xF_g1 0xF_g2; do MRINR_LIB=build/libmrinr_morlet_$m.so timeout 120 python tools/morlet_bench.py >> $O/e_morlet.txt 2>&1; done
+for m in 0x0 0xA 0xF 0x5_g1 0x5_g2 0xF_g1 0xF_g2 0x5_w16 0xF_w16; do MRINR_LIB=build/libmrinr_morlet_$m.so timeout 120 python tools/morlet_bench.py >> $O/e_morlet.txt 2>&1; done
 timeout 120 python tools/morlet_bench.py >> $O/e_morlet.txt 2>&1
 cat $O/e_morlet.txt
 echo "== training step timing"; timeout 200 python tools/train_bench.py > $O/e_train_bench.txt 2>&1; echo "rc=$?"; cat $O/e_train_bench.txt

@@ -40,49 +40,70 @@ __device__ __forceinline__ int reflect_idx(int t, int n) {
   return t >= n ? 2 * (n - 1) - t : t;
 }
 
+// Persistent form: a warp walks patches warp, warp + n_warps, ... (a few thousand CTAs' worth of launch and drain cost
+// was the difference between 0.73 and the copy roofline for 52 800 short-lived CTAs); for the baseline geometry
+// (O = 32: 8 float4 per lane) all 8 loads of a patch are issued before the first store.
+template <int NQ>      // float4 per lane and patch (O*O/128) when known at compile time, 0 = generic
 __global__ void __launch_bounds__(256)
 image_to_patches_kernel(const float* __restrict__ img, long long n_patches, int H, int W, int O, int I,
                         int nV, int nH, float* __restrict__ patches, uint8_t* __restrict__ black) {
   const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= n_patches) return;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int per_img = nV * nH;
-  const long long n = warp / per_img;
-  const int p = (int)(warp - n * per_img);
-  const int py = p / nH, px = p - py * nH;
   const int pad = (O - I) / 2;
-  const float* src = img + n * (long long)H * W;
-  float4* dst = reinterpret_cast<float4*>(patches + warp * (long long)O * O);
   const int q_per_row = O / 4;
   const int total_q = O * q_per_row;
-  const int y0 = I * py - pad, x0 = I * px - pad;
   // x0 + s is a multiple of 4 when I and pad are; rows are 16-byte aligned when W is a multiple of 4
   const bool vec_ok = ((I | pad | W) & 3) == 0 && aligned16(img);
-  float sum = 0.f;
-#pragma unroll 4
-  for (int q = lane; q < total_q; q += 32) {
-    const int r = q / q_per_row;
-    const int s = (q - r * q_per_row) * 4;
-    const float* row = src + (long long)reflect_idx(y0 + r, H) * W;
-    float4 v;
-    const int xs = x0 + s;
-    if (vec_ok && xs >= 0 && xs + 3 < W) {
-      v = __ldg(reinterpret_cast<const float4*>(row + xs));      // interior: one aligned 16-byte load
-    } else {
-      v.x = __ldg(row + reflect_idx(xs + 0, W));
-      v.y = __ldg(row + reflect_idx(xs + 1, W));
-      v.z = __ldg(row + reflect_idx(xs + 2, W));
-      v.w = __ldg(row + reflect_idx(xs + 3, W));
-    }
-    dst[q] = v;
-    sum += (v.x + v.y) + (v.z + v.w);
-  }
-  if (black != nullptr) {
+  for (long long warp = warp0; warp < n_patches; warp += n_warps) {
+    const long long n = warp / per_img;
+    const int p = (int)(warp - n * per_img);
+    const int py = p / nH, px = p - py * nH;
+    const float* src = img + n * (long long)H * W;
+    float4* dst = reinterpret_cast<float4*>(patches + warp * (long long)O * O);
+    const int y0 = I * py - pad, x0 = I * px - pad;
+    auto load_q = [&](int q) -> float4 {
+      const int r = q / q_per_row;
+      const int s = (q - r * q_per_row) * 4;
+      const float* row = src + (long long)reflect_idx(y0 + r, H) * W;
+      float4 v;
+      const int xs = x0 + s;
+      if (vec_ok && xs >= 0 && xs + 3 < W) {
+        v = __ldg(reinterpret_cast<const float4*>(row + xs));      // interior: one aligned 16-byte load
+      } else {
+        v.x = __ldg(row + reflect_idx(xs + 0, W));
+        v.y = __ldg(row + reflect_idx(xs + 1, W));
+        v.z = __ldg(row + reflect_idx(xs + 2, W));
+        v.w = __ldg(row + reflect_idx(xs + 3, W));
+      }
+      return v;
+    };
+    float sum = 0.f;
+    if (NQ > 0) {
+      float4 v[NQ > 0 ? NQ : 1];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    // tile.mean() < 1e-10 (tiling.py:194-195); the summation order differs from torch's, which can
-    // only matter for a patch whose sum is within rounding of O*O*1e-10.
-    if (lane == 0) black[warp] = (sum / (float)(O * O) < 1e-10f) ? 1 : 0;
+      for (int k = 0; k < NQ; ++k) v[k] = load_q(lane + 32 * k);
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        __stcs(dst + lane + 32 * k, v[k]);            // written once, read once by the encoder: streaming store
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    } else {
+#pragma unroll 4
+      for (int q = lane; q < total_q; q += 32) {
+        const float4 v = load_q(q);
+        dst[q] = v;
+        sum += (v.x + v.y) + (v.z + v.w);
+      }
+    }
+    if (black != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      // tile.mean() < 1e-10 (tiling.py:194-195); the summation order differs from torch's, which can
+      // only matter for a patch whose sum is within rounding of O*O*1e-10.
+      if (lane == 0) black[warp] = (sum / (float)(O * O) < 1e-10f) ? 1 : 0;
+    }
   }
 }
 
@@ -321,7 +342,16 @@ minmax_reduce_kernel(const float* __restrict__ in, long long n, unsigned int* __
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if ((n & 3) == 0 && aligned16(src)) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
-    for (; i < n / 4; i += stride) {
+    const long long n4 = n / 4;
+    for (; i + 3 * stride < n4; i += 4 * stride) {            // four independent 16-byte loads in flight
+      const float4 a = __ldg(s4 + i), b = __ldg(s4 + i + stride), c = __ldg(s4 + i + 2 * stride),
+                   d = __ldg(s4 + i + 3 * stride);
+      mn = fminf(fminf(fminf(mn, fminf(a.x, a.y)), fminf(fminf(a.z, a.w), fminf(b.x, b.y))),
+                 fminf(fminf(fminf(b.z, b.w), fminf(c.x, c.y)), fminf(fminf(c.z, c.w), fminf(fminf(d.x, d.y), fminf(d.z, d.w)))));
+      mx = fmaxf(fmaxf(fmaxf(mx, fmaxf(a.x, a.y)), fmaxf(fmaxf(a.z, a.w), fmaxf(b.x, b.y))),
+                 fmaxf(fmaxf(fmaxf(b.z, b.w), fmaxf(c.x, c.y)), fmaxf(fmaxf(c.z, c.w), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w)))));
+    }
+    for (; i < n4; i += stride) {
       const float4 v = __ldg(s4 + i);
       mn = fminf(fminf(mn, v.x), fminf(fminf(v.y, v.z), v.w));
       mx = fmaxf(fmaxf(mx, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
@@ -358,14 +388,20 @@ minmax_apply_kernel(const float* __restrict__ in, long long n, const unsigned in
   if ((n & 3) == 0 && aligned16(src) && aligned16(dst)) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
-    for (; i < n / 4; i += stride) {
-      float4 v = __ldg(s4 + i);
+    const long long n4 = n / 4;
+    auto norm4 = [&](float4 v) {
       v.x = __fdiv_rn(__fsub_rn(v.x, mn), range);
       v.y = __fdiv_rn(__fsub_rn(v.y, mn), range);
       v.z = __fdiv_rn(__fsub_rn(v.z, mn), range);
       v.w = __fdiv_rn(__fsub_rn(v.w, mn), range);
-      d4[i] = v;
+      return v;
+    };
+    for (; i + 3 * stride < n4; i += 4 * stride) {            // four independent 16-byte loads in flight
+      const float4 a = __ldg(s4 + i), b = __ldg(s4 + i + stride), c = __ldg(s4 + i + 2 * stride),
+                   d = __ldg(s4 + i + 3 * stride);
+      d4[i] = norm4(a); d4[i + stride] = norm4(b); d4[i + 2 * stride] = norm4(c); d4[i + 3 * stride] = norm4(d);
     }
+    for (; i < n4; i += stride) d4[i] = norm4(__ldg(s4 + i));
   } else {
     for (; i < n; i += stride) dst[i] = __fdiv_rn(__fsub_rn(__ldg(src + i), mn), range);
   }
@@ -502,9 +538,17 @@ extern "C" int mrinr_image_to_patches(const float* d_img, int64_t N, int32_t H, 
   if (N == 0) return 0;
   const int nV = (H + vpad) / I, nH = (W + hpad) / I;
   const long long n_patches = (long long)N * nV * nH;
-  const long long threads = n_patches * 32;
-  image_to_patches_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      d_img, n_patches, H, W, O, I, nV, nH, d_patches, d_black);
+  // persistent grid: 8 warps per CTA, up to 16 CTAs' worth of warps per SM; a warp walks patches with that stride
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long ctas = (n_patches + 7) / 8;
+  if (ctas > (long long)sms * 16) ctas = (long long)sms * 16;
+  if (O == 32)
+    image_to_patches_kernel<8><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(d_img, n_patches, H, W, O, I, nV, nH,
+                                                                               d_patches, d_black);
+  else
+    image_to_patches_kernel<0><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(d_img, n_patches, H, W, O, I, nV, nH,
+                                                                               d_patches, d_black);
   count_launch();
   return check_launch("image_to_patches");
 }
@@ -535,6 +579,9 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
     const long long per_img = n_quads / N;
     if (I == 16 && (K == 24 || K == 32) && per_img < (1ll << 30)) {
       // a thread walks several images (same pixel position: the window arithmetic and the weights are reused)
+      // four images per thread.  (Measured in round 2: fewer, longer-lived CTAs -- ~16 per SM, 44 images per thread,
+      // which helped image_to_patches and minmax -- make this gather SLOWER: 0.62 instead of 0.69 weighted, 0.89
+      // instead of 1.01 unit; it lives on many CTAs' worth of independent loads in flight.)
       long long gy = (N + 3) / 4;
       if (gy > 65535) gy = 65535;
       dim3 grid((unsigned)((per_img + 255) / 256), (unsigned)gy);
@@ -583,9 +630,12 @@ extern "C" int mrinr_minmax_normalize(const float* d_in, int64_t G, int64_t n, f
   cudaStream_t st = (cudaStream_t)stream;
   unsigned int* scr = reinterpret_cast<unsigned int*>(d_scratch);
   minmax_init_kernel<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(scr, G);
-  long long bx = (n / 4 + 255) / 256;
+  // about 16 CTAs per SM over all groups, at least 4 float4 per thread: 96 volumes x 592 CTAs of one or two loads per
+  // thread each (round 1) spent their time in launch / drain and one atomic per CTA (0.68 of the copy roofline)
+  long long bx = (n / 4 + 1023) / 1024;
+  const long long bx_cap = (148LL * 16 + G - 1) / G;
+  if (bx > bx_cap) bx = bx_cap;
   if (bx < 1) bx = 1;
-  if (bx > 592) bx = 592;   // 4 CTAs per SM x 148
   dim3 grid((unsigned)bx, (unsigned)G);
   minmax_reduce_kernel<<<grid, 256, 0, st>>>(d_in, n, scr);
   minmax_apply_kernel<<<grid, 256, 0, st>>>(d_in, n, scr, d_out);

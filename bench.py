@@ -44,10 +44,9 @@ PATCHES_PER_SLICE, COORDS_PER_PATCH = 400, 576
 FLOP_PER_LAYER_COORD = 2 * 256 * 256                     # one tensor-eligible hidden contraction
 METRIC = "reconstructed 320x320 slices/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of the synthesis kernel from the ncu --set full capture in
-# profiles/r01_ncu_siren_v5_final.txt (136.34 MB + 40.60 MB for 64 slices, the v5 kernel with sub-block walking);
-# algorithmic: 400 x 5 KB of modulations read + 400 x 2304 B of outputs written per slice = 2.97 MB (part of the
-# output is still in L2 when the kernel ends)
-DRAM_TRAFFIC_BYTES_PER_SLICE = (136.34e6 + 40.60e6) / 64
+# profiles/r02_ncu_siren_sine.txt (518.75 MB + 199.19 MB for one 235-slice launch of this bench);
+# algorithmic: 400 x 5 KB of modulations read + 400 x 2304 B of outputs written per slice = 2.97 MB (ratio 1.03)
+DRAM_TRAFFIC_BYTES_PER_SLICE = (518.75e6 + 199.19e6) / 235
 MODEL_KW = dict(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=1.0, w0_initial=30.0,
                 use_bias=True, dropout=0.1, modulate=True, encoder_type="custom", encoder_path=None,
                 outer_patch_size=32, inner_patch_size=16, siren_patch_size=24)
@@ -519,7 +518,7 @@ def run_ours(args):
                          "frac": achieved / peak if peak else None,
                          "traffic": DRAM_TRAFFIC_BYTES_PER_SLICE * kern_patches / PATCHES_PER_SLICE / max(len(events), 1)
                          if (L == 5) else None,
-                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_ncu_siren_v5_final.txt (64 slices)",
+                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r02_ncu_siren_sine.txt (one 235-slice launch)",
                          "kernel": "siren_tc5_kernel (fused modulated-SIREN MLP, tcgen05 cta_group::2)", "peak_source": f"{peak_src}, sustained bf16",
                          "flop_per_coord": flop_per_coord, "patches_billed": kern_patches,
                          "patches_handed": kern_patches_handed,
@@ -528,7 +527,7 @@ def run_ours(args):
                          "kernel_ms_per_step": kern_ms / args.steps, "kernel_launches_timed": len(events),
                          "kernel_share_of_step": kern_ms / ms_total,
                          "single_launch_after_idle_tflops": burst,
-                         "note": "the sustained figure is limited by the 1 kW power cap (clocks.reasons), see profiles/r01_siren.md"},
+                         "note": "the sustained figure is limited by the 1 kW power cap (clocks.reasons), see profiles/r02_siren.md"},
             "clocks": clocks,
         }
         if cpu is not None:

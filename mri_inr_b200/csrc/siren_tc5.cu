@@ -134,15 +134,15 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
 // (one MUFU.SIN per activation already) and the FMA pipe are both close to their limits in the Morlet epilogue, so the
 // envelope is split between them: groups whose bit is set in kMorletFmaMask use the FMA-pipe evaluation (gauss2),
 // the others ex2.approx on the special-function unit.  Measured, sustained TFLOP/s of the kernel on dense modulations
-// (profiles/r02_morlet_variants.txt): all MUFU (round 1) 792, all FMA 773, groups 0 and 2 on the FMA pipe 820.
+// (profiles/r02_morlet_variants.txt): all MUFU (round 1) 792-805, all FMA 773-780, groups 0 and 2 on the FMA pipe
+// 820-831 (0xA the same; 0x1 802, 0x7 804).  Also measured and NOT better: free instruction scheduling of the envelope
+// (831), an Estrin polynomial (811), and a software-pipelined all-FMA version -- four packed chains advanced stage by
+// stage with the next block's MUFU.SIN between the stages -- 767: the packed FMAs are throughput-, not latency-bound
+// (an FFMA2 occupies the 32-lane FMA pipe for two issue cycles; ~10 packed operations per activation pair).
 #ifndef MRINR_MORLET_FMA_MASK
 #define MRINR_MORLET_FMA_MASK 0x5
 #endif
 constexpr int kMorletFmaMask = MRINR_MORLET_FMA_MASK;
-#ifndef MRINR_MORLET_PIPE
-#define MRINR_MORLET_PIPE 0
-#endif
-constexpr bool kMorletPipe = MRINR_MORLET_PIPE != 0;      // hidden phases: the stage-interleaved all-FMA envelope
 __device__ __forceinline__ uint64_t morlet_env2(int g, float x0, float x1) {
   if ((kMorletFmaMask >> g) & 1) return gauss2(x0, x1);
   float t0, t1;
@@ -311,86 +311,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
       }
       finish_group(3);
     };
-    // Morlet, software-pipelined (MRINR_MORLET_PIPE): the envelope of 8 activations at a time as FOUR packed chains
-    // advanced stage by stage (a warp issues in order and the epilogue has two warps per SM sub-partition: one chain of
-    // ten dependent packed FMAs pays the 4-cycle latency at every step), with the eight MUFU.SIN of the NEXT eight
-    // activations dropped in between the stages -- one special-function instruction per ~8 FMA-pipe instructions, which
-    // is the ratio at which neither unit waits for the other.
-    // envelope of activations b0 .. b0+7 of a 16-activation chunk -> G[4] (packed pairs); with `next_sines` the sines of
-    // activations 8 .. 15 are issued between the stages
-    auto morlet_block8 = [&](const uint32_t (&v)[16], int b0, bool next_sines, float (&s)[16], uint64_t (&G)[4]) {
-      auto SIN = [&](int k) {
-        if (next_sines) {
-          const float x = __uint_as_float(v[8 + k]);
-          s[8 + k] = vsin(W0ONE ? x : P.w0 * x);
-        }
-      };
-      uint64_t T[4], Z[4], F[4], Pp[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint64_t X = pk2(__uint_as_float(v[b0 + 2 * c]), __uint_as_float(v[b0 + 2 * c + 1]));
-        T[c] = gmul2(X, X);
-      }
-      SIN(0);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float t0, t1;
-        upk2(T[c], t0, t1);
-        T[c] = pk2(fminf(t0, 174.0f), fminf(t1, 174.0f));
-      }
-      SIN(1);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Z[c] = gfma2(T[c], 0xBF38AA3BBF38AA3BULL, 0x4B4000004B400000ULL);
-      SIN(2);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) F[c] = gsub2(0x4B4000004B400000ULL, Z[c]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) F[c] = gfma2(T[c], 0xBF38AA3BBF38AA3BULL, F[c]);
-      SIN(3);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Pp[c] = gfma2(0x3C1CCBEA3C1CCBEAULL, F[c], 0x3D650A203D650A20ULL);
-      SIN(4);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Pp[c] = gfma2(Pp[c], F[c], 0x3E76036D3E76036DULL);
-      SIN(5);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Pp[c] = gfma2(Pp[c], F[c], 0x3F31706E3F31706EULL);
-      SIN(6);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Pp[c] = gfma2(Pp[c], F[c], 0x3F7FFFF43F7FFFF4ULL);
-      SIN(7);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float p0, p1, z0, z1;
-        upk2(Pp[c], p0, p1);
-        upk2(Z[c], z0, z1);
-        G[c] = pk2(__int_as_float(__float_as_int(p0) + (__float_as_int(z0) << 23)),
-                   __int_as_float(__float_as_int(p1) + (__float_as_int(z1) << 23)));
-      }
-    };
-    auto morlet16_pipe = [&](const uint32_t (&v)[16], const float4 (&m)[4], uint32_t (&pk)[8], uint32_t (&lo)[8]) {
-      float s[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x = __uint_as_float(v[i]);
-        s[i] = vsin(W0ONE ? x : P.w0 * x);
-      }
-#pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        const int b0 = blk * 8;
-        uint64_t G[4];
-        morlet_block8(v, b0, blk == 0, s, G);
-        float a[8];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 mm = m[blk * 2 + (c >> 1)];
-          const uint64_t M2 = (c & 1) ? pk2(mm.z, mm.w) : pk2(mm.x, mm.y);
-          upk2(vmul2(G[c], vmul2(pk2(s[b0 + 2 * c], s[b0 + 2 * c + 1]), M2)), a[2 * c], a[2 * c + 1]);
-        }
-        emit4(blk * 2 + 0, a[0], a[1], a[2], a[3], pk, lo);
-        emit4(blk * 2 + 1, a[4], a[5], a[6], a[7], pk, lo);
-      }
-    };
     // operand entries of columns cg*kCols + hc*16 .. +15 of row t: pk into slot's A buffer; X3: lo into the second one
     auto store16 = [&](int slot, int hc, const uint32_t (&pk)[8], const uint32_t (&lo)[8]) {
       uint8_t* base = smem + kOffA + slot * 65536 + (cg * (kCols / 8) + hc * 2) * 2048 + t * 16;
@@ -450,38 +370,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
           }
         }
       };
-      // the same chunk with the stage-interleaved Morlet envelope (see morlet16_pipe)
-      auto dot16_pipe = [&](const uint32_t (&v)[16], int hc) {
-        float4 mw[4];
-        load4x4(mp, hc, mw);
-        float s[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x = __uint_as_float(v[i]);
-          s[i] = vsin(W0ONE ? x : P.w0 * x);
-        }
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          const int b0 = blk * 8;
-          uint64_t G[4];
-          morlet_block8(v, b0, blk == 0, s, G);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 mm = mw[blk * 2 + (c >> 1)];
-            const uint64_t M2 = (c & 1) ? pk2(mm.z, mm.w) : pk2(mm.x, mm.y);
-            const uint64_t hh = vmul2(G[c], pk2(s[b0 + 2 * c], s[b0 + 2 * c + 1]));
-            if (c & 1) d23 = vfma2(hh, M2, d23); else d01 = vfma2(hh, M2, d01);
-          }
-        }
-      };
 #pragma unroll 1
       for (int hp = 0; hp < kPairs; ++hp) {
         tmem_ld_wait();
         tmem_ld16(tcol + (uint32_t)(hp * 2 + 1) * 16u, vb);
-        if (ACT == MRINR_ACT_MORLET && kMorletPipe) dot16_pipe(va, hp * 2); else dot16(va, hp * 2);
+        dot16(va, hp * 2);
         tmem_ld_wait();
         if (hp < kPairs - 1) tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
-        if (ACT == MRINR_ACT_MORLET && kMorletPipe) dot16_pipe(vb, hp * 2 + 1); else dot16(vb, hp * 2 + 1);
+        dot16(vb, hp * 2 + 1);
       }
       TL(1020 + slot);
       tc_fence_before();
@@ -620,12 +516,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
             tmem_ld_wait();
             tmem_ld16(tcol + (uint32_t)(hp * 2 + 1) * 16u, vb);     // next chunk lands while this one is processed
             load4x4(mp, hp * 2, m);
-            if (ACT == MRINR_ACT_MORLET && kMorletPipe) morlet16_pipe(va, m, pk, lo); else act16_pack(va, m, pk, lo);
+            act16_pack(va, m, pk, lo);
             store16(slot, hp * 2, pk, lo);
             tmem_ld_wait();
             if (hp < kPairs - 1) tmem_ld16(tcol + (uint32_t)(hp * 2 + 2) * 16u, va);
             load4x4(mp, hp * 2 + 1, m);
-            if (ACT == MRINR_ACT_MORLET && kMorletPipe) morlet16_pipe(vb, m, pk, lo); else act16_pack(vb, m, pk, lo);
+            act16_pack(vb, m, pk, lo);
             store16(slot, hp * 2 + 1, pk, lo);
           }
           tc_fence_before();

@@ -372,18 +372,7 @@ __device__ __forceinline__ uint64_t vfma2(uint64_t a, uint64_t b, uint64_t c) {
 // magic-number trick, degree-4 polynomial of the fraction in [-0.5, 0.5] (relative error 2.6e-6; coefficients fitted
 // for minimal relative error, checked in tests/test_host_logic.py), exponent added with an integer shift-add.
 // x^2 is clamped at 174 (|x| > 13.2 -> ~1e-38 instead of a wrapped exponent).
-// MRINR_GAUSS_SCHED: 0 = order-pinned (volatile) Horner, 1 = free scheduling (ptxas may interleave the two pairs of a
-// group and the neighbouring MUFU work), 2 = free scheduling + Estrin (shorter dependency chain, one more FMUL2).
-// The epilogue runs two warps per SM sub-partition, so a 10-deep chain of dependent packed FMAs is latency-, not
-// throughput-bound; measured in profiles/r02_morlet_variants.txt.
-#ifndef MRINR_GAUSS_SCHED
-#define MRINR_GAUSS_SCHED 0
-#endif
-#if MRINR_GAUSS_SCHED == 0
 #define GAUSS_ASM asm volatile
-#else
-#define GAUSS_ASM asm
-#endif
 __device__ __forceinline__ uint64_t gmul2(uint64_t a, uint64_t b) {
   uint64_t r;
   GAUSS_ASM("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -410,17 +399,10 @@ __device__ __forceinline__ uint64_t gauss2(float x0, float x1) {
   const uint64_t Z = gfma2(T, NEGC, 0x4B4000004B400000ULL);        // + 1.5 * 2^23: round(y) in the low mantissa bits
   const uint64_t NNEG = gsub2(0x4B4000004B400000ULL, Z);           // -n, n = round(y)
   const uint64_t F = gfma2(T, NEGC, NNEG);                         // y - n  in [-0.5, 0.5]
-#if MRINR_GAUSS_SCHED == 2
-  const uint64_t F2 = gmul2(F, F);                                 // Estrin: (c0 + c1 f) + f^2 ((c2 + c3 f) + c4 f^2)
-  const uint64_t lo = gfma2(0x3F31706E3F31706EULL, F, 0x3F7FFFF43F7FFFF4ULL);
-  const uint64_t hi = gfma2(0x3D650A203D650A20ULL, F, 0x3E76036D3E76036DULL);
-  const uint64_t Pp = gfma2(gfma2(0x3C1CCBEA3C1CCBEAULL, F2, hi), F2, lo);
-#else
   uint64_t Pp = gfma2(0x3C1CCBEA3C1CCBEAULL, F, 0x3D650A203D650A20ULL);
   Pp = gfma2(Pp, F, 0x3E76036D3E76036DULL);
   Pp = gfma2(Pp, F, 0x3F31706E3F31706EULL);
   Pp = gfma2(Pp, F, 0x3F7FFFF43F7FFFF4ULL);
-#endif
   float p0, p1, z0, z1;
   upk2(Pp, p0, p1);
   upk2(Z, z0, z1);

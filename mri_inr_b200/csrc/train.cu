@@ -91,16 +91,21 @@ __global__ void layer0_pre_kernel(const float* __restrict__ grid, const float* _
 }
 
 // h[m][j] = drop(act(pre)) * mod[b][j];  pre = pre0[c][j] for layer 0 (patch independent), else pre[m][j]
-__global__ void act_fwd_kernel(const float* __restrict__ pre, int layer0, const float* __restrict__ mod, long long M, int C,
-                               float w0, int morlet, Drop drop, int layer, float* __restrict__ h) {
+// grid (patch, coordinate chunk), thread = feature j: rows are read and written coalesced, no index divisions
+constexpr int kChunks = 4;      // coordinate chunks per patch (CTAs per patch) of the element-wise kernels
+__global__ void __launch_bounds__(kH) act_fwd_kernel(const float* __restrict__ pre, int layer0, const float* __restrict__ mod,
+                                                     long long M, int C, float w0, int morlet, Drop drop, int layer,
+                                                     float* __restrict__ h) {
+  const long long b = blockIdx.x;
+  const int j = threadIdx.x;
+  const int per = (C + kChunks - 1) / kChunks;
+  const int c0 = blockIdx.y * per, c1 = min(C, c0 + per);
   const long long total = M * kH;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long m = idx >> 8;
-    const int j = (int)(idx & 255);
-    const long long b = m / C;
-    const int c = (int)(m - b * C);
+  const float mj = mod[b * kH + j];
+  for (int c = c0; c < c1; ++c) {
+    const long long idx = (b * C + c) * kH + j;
     const float z = layer0 ? pre[(long long)c * kH + j] : pre[idx];
-    h[idx] = act_f(z, w0, morlet) * keep_scale(drop, layer, idx, total) * mod[b * kH + j];
+    h[idx] = act_f(z, w0, morlet) * keep_scale(drop, layer, idx, total) * mj;
   }
 }
 
@@ -129,16 +134,18 @@ __global__ void out_fwd_kernel(const float* __restrict__ h, const float* __restr
   }
 }
 
-// one CTA per patch, thread = feature j:  g = dy w0 cos(w0 pre_last);  dh = g w_last;  dw_last += g h;  db_last += g
+// grid (patch, coordinate chunk), thread = feature j:  g = dy w0 cos(w0 pre_last);  dh = g w_last;  dw_last += g h;  db_last += g
 __global__ void __launch_bounds__(kH) out_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre_last,
                                                      const float* __restrict__ h, const float* __restrict__ w_last, int C,
                                                      float w0, float grad_scale, float* __restrict__ dh,
                                                      float* __restrict__ dw_last, float* __restrict__ db_last) {
   const long long b = blockIdx.x;
   const int j = threadIdx.x;
+  const int per = (C + kChunks - 1) / kChunks;
+  const int c0 = blockIdx.y * per, c1 = min(C, c0 + per);
   const float wl = w_last[j];
   float accw = 0.f, accb = 0.f;
-  for (int c = 0; c < C; ++c) {
+  for (int c = c0; c < c1; ++c) {
     const long long m = b * C + c;
     const float g = dy[m] * grad_scale * w0 * cosf(w0 * pre_last[m]);
     dh[m * kH + j] = g * wl;
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(kH) out_bwd_kernel(const float* __restrict__ d
   if (db_last && j == 0) atomicAdd(db_last, accb);
 }
 
-// one CTA per patch, thread = feature j.  In: dh (gradient w.r.t. h_l).  Out (in place): dz (gradient w.r.t. the
+// grid (patch, coordinate chunk), thread = feature j.  In: dh (gradient w.r.t. h_l).  Out (in place): dz (gradient w.r.t. the
 // pre-activation);  dmod[b][j] = sum_c dh * drop(act);  db[j] += sum dz;  layer 0 also: dW_0[j][0..1] += sum dz * g_c.
 __global__ void __launch_bounds__(kH) act_bwd_kernel(float* __restrict__ dh, const float* __restrict__ pre, int layer0,
                                                      const float* __restrict__ mod, const float* __restrict__ grid, int C,
@@ -158,10 +165,12 @@ __global__ void __launch_bounds__(kH) act_bwd_kernel(float* __restrict__ dh, con
                                                      float* __restrict__ dw0) {
   const long long b = blockIdx.x;
   const int j = threadIdx.x;
+  const int per = (C + kChunks - 1) / kChunks;
+  const int c0 = blockIdx.y * per, c1 = min(C, c0 + per);
   const float mj = mod[b * kH + j];
   const long long total = M * kH;
   float accm = 0.f, accb = 0.f, accx = 0.f, accy = 0.f;
-  for (int c = 0; c < C; ++c) {
+  for (int c = c0; c < c1; ++c) {
     const long long idx = (b * C + c) * kH + j;
     const float z = layer0 ? pre[(long long)c * kH + j] : pre[idx];
     float a, da;
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(kH) act_bwd_kernel(float* __restrict__ dh, con
       accy = fmaf(dz, grid[2 * c + 1], accy);
     }
   }
-  dmod[b * kH + j] = accm;
+  atomicAdd(dmod + b * kH + j, accm);         // kChunks partial sums per element (dmod is zero-initialised)
   if (db) atomicAdd(db + j, accb);
   if (layer0 && dw0) {
     atomicAdd(dw0 + 2 * j, accx);
@@ -186,15 +195,16 @@ __global__ void __launch_bounds__(kH) act_bwd_kernel(float* __restrict__ dh, con
 }
 
 // ---- C[Na,Nb] += A[M,Na]^T B[M,Nb]  (reduction over the M rows; split over row ranges, fp32 atomics) ---------------
-constexpr int kGT = 128, kGK = 8, kGRows = 1024;
+constexpr int kGT = 128, kGK = 8;
 __global__ void __launch_bounds__(256) gemm_tn_atomic_kernel(const float* __restrict__ A, long long lda, int Na,
                                                              const float* __restrict__ Bm, long long ldb, int Nb,
-                                                             long long M, float* __restrict__ Cm, long long ldc) {
+                                                             long long M, int rows_per_cta, float* __restrict__ Cm,
+                                                             long long ldc) {
   __shared__ __align__(16) float As[kGK][kGT];
   __shared__ __align__(16) float Bs[kGK][kGT];
   const int a0 = blockIdx.x * kGT, b0 = blockIdx.y * kGT;
-  const long long m0 = (long long)blockIdx.z * kGRows;
-  const long long m1 = m0 + kGRows < M ? m0 + kGRows : M;
+  const long long m0 = (long long)blockIdx.z * rows_per_cta;
+  const long long m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
   const int t = threadIdx.x;
   const int tx = t & 15, ty = t >> 4;          // 16 x 16 threads, 8 x 8 outputs each: rows ty*4+{0..3}, 64+ty*4+{0..3}
   const int lr = t >> 5, lc = (t & 31) * 4;    // loader: row lr of the K slab, 4 consecutive columns
@@ -259,8 +269,14 @@ static int gemm_tn_atomic(const float* A, long long lda, int Na, const float* Bm
   if (M <= 0 || !Cm) return 0;
   MRINR_REQUIRE(aligned16(A) && aligned16(Bm) && lda % 4 == 0 && ldb % 4 == 0, MRINR_E_ALIGN,
                 "gemm_tn: operands must be 16-byte aligned with row strides that are multiples of 4");
-  dim3 grid((Na + kGT - 1) / kGT, (Nb + kGT - 1) / kGT, (unsigned)((M + kGRows - 1) / kGRows));
-  gemm_tn_atomic_kernel<<<grid, 256, 0, st>>>(A, lda, Na, Bm, ldb, Nb, M, Cm, ldc);
+  // slices of the reduction per output tile: enough CTAs to fill the GPU twice, at least 32 rows each
+  const int tiles = ((Na + kGT - 1) / kGT) * ((Nb + kGT - 1) / kGT);
+  long long slices = (2 * 148 + tiles - 1) / tiles;
+  if (slices > (M + 31) / 32) slices = (M + 31) / 32;
+  if (slices < 1) slices = 1;
+  const int rows = (int)(((M + slices - 1) / slices + kGK - 1) / kGK * kGK);
+  dim3 grid((Na + kGT - 1) / kGT, (Nb + kGT - 1) / kGT, (unsigned)((M + rows - 1) / rows));
+  gemm_tn_atomic_kernel<<<grid, 256, 0, st>>>(A, lda, Na, Bm, ldb, Nb, M, rows, Cm, ldc);
   count_launch();
   return check_launch("gemm_tn_atomic");
 }
@@ -545,8 +561,8 @@ extern "C" int mrinr_train_forward(const MrinrPacked* p, const MrinrWeightsView*
                                                           v->d_net_bias ? v->d_net_bias[0] : nullptr, C, ws + w.pre0);
   count_launch();
   if ((rc = check_launch("layer0_pre")) != 0) return rc;
-  const unsigned ew_grid = (unsigned)((M * kH / 256 < 148 * 16) ? (M * kH + 255) / 256 : 148 * 16);
-  act_fwd_kernel<<<ew_grid, 256, 0, st>>>(ws + w.pre0, 1, ws + w.mods, M, C, p->w0_initial, morlet, drop, 0, ws + w.h);
+  const dim3 ew_grid((unsigned)B, kChunks);
+  act_fwd_kernel<<<ew_grid, kH, 0, st>>>(ws + w.pre0, 1, ws + w.mods, M, C, p->w0_initial, morlet, drop, 0, ws + w.h);
   count_launch();
   if ((rc = check_launch("act_fwd")) != 0) return rc;
   for (int l = 1; l < L; ++l) {
@@ -556,8 +572,8 @@ extern "C" int mrinr_train_forward(const MrinrPacked* p, const MrinrWeightsView*
     rc = launch_dense_split(ws + w.h + (size_t)(l - 1) * hs, kH, kH, nullptr, 0, 0, pk,
                             v->d_net_bias ? v->d_net_bias[l] : nullptr, kH, 0, 0.f, pre, kH, M, p->d_errflag, st);
     if (rc != 0) return rc;
-    act_fwd_kernel<<<ew_grid, 256, 0, st>>>(pre, 0, ws + w.mods + (size_t)l * B * kH, M, C, p->w0, morlet, drop, l,
-                                           ws + w.h + (size_t)l * hs);
+    act_fwd_kernel<<<ew_grid, kH, 0, st>>>(pre, 0, ws + w.mods + (size_t)l * B * kH, M, C, p->w0, morlet, drop, l,
+                                          ws + w.h + (size_t)l * hs);
     count_launch();
     if ((rc = check_launch("act_fwd")) != 0) return rc;
   }
@@ -601,7 +617,9 @@ extern "C" int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView
   // ---- output layer
   float* cur = ws + w.dA;      // gradient w.r.t. h_l, then (in place) w.r.t. the pre-activation of layer l
   float* nxt = ws + w.dB;
-  out_bwd_kernel<<<(unsigned)B, kH, 0, st>>>(d_dout, ws + w.pre_last, ws + w.h + (size_t)(L - 1) * hs, v->d_last_weight,
+  MRINR_CUDA(cudaMemsetAsync(ws + w.dmods, 0, (size_t)L * B * kH * sizeof(float), st));
+  const dim3 ew_grid((unsigned)B, kChunks);
+  out_bwd_kernel<<<ew_grid, kH, 0, st>>>(d_dout, ws + w.pre_last, ws + w.h + (size_t)(L - 1) * hs, v->d_last_weight,
                                             C, p->w0, grad_scale, cur, (float*)grads->d_last_weight,
                                             (float*)grads->d_last_bias);
   count_launch();
@@ -609,7 +627,7 @@ extern "C" int mrinr_train_backward(const MrinrPacked* p, const MrinrWeightsView
   // ---- synthesis layers L-1 .. 0
   for (int l = L - 1; l >= 0; --l) {
     const float* pre = l == 0 ? ws + w.pre0 : ws + w.pre + (size_t)(l - 1) * hs;
-    act_bwd_kernel<<<(unsigned)B, kH, 0, st>>>(cur, pre, l == 0, ws + w.mods + (size_t)l * B * kH, v->d_grid, C, M,
+    act_bwd_kernel<<<ew_grid, kH, 0, st>>>(cur, pre, l == 0, ws + w.mods + (size_t)l * B * kH, v->d_grid, C, M,
                                               l == 0 ? p->w0_initial : p->w0, morlet, drop, l,
                                               ws + w.dmods + (size_t)l * B * kH, g_net_b ? g_net_b[l] : nullptr,
                                               l == 0 && g_net_w ? g_net_w[0] : nullptr);

@@ -320,6 +320,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) siren_t
         return;
       }
 #endif
+#ifdef MRINR_POWER_CONST_A     // tools/power_split.py only: the stores execute, but with constant data (separates the
+      {                        // energy of the stores from the energy of operand bits toggling in the tensor core)
+        asm volatile("" ::"r"(pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7]));
+        const uint4 c = make_uint4(0x2e662e66u, 0x2e662e66u, 0x2e662e66u, 0x2e662e66u);      // 0.1 in fp16
+        *reinterpret_cast<uint4*>(base) = c;
+        *reinterpret_cast<uint4*>(base + 2048) = c;
+        return;
+      }
+#endif
       *reinterpret_cast<uint4*>(base) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(base + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       if (X3) {

@@ -158,3 +158,29 @@ def test_training_side_tiling_helpers():
     assert fu.shape[0] == 7 and torch.equal(ff, f[[0, 2, 3, 5, 6, 7, 8]])
     c = tiling.extract_center_batch(f, 32, 24)
     assert c.shape == (9, 24, 24) and torch.equal(c, f[:, 4:28, 4:28])
+
+
+def test_training_without_biases_and_w0_2():
+    """use_bias=False (no bias parameters: the gradient view carries null pointers) and a hidden w0 of 2 (the activation
+    derivative is w0 cos(w0 z)), against the CPU restatement."""
+    from mri_inr_b200.modulated_siren import ModulatedSiren
+
+    p, B = 0.1, 3
+    sd = osiren.synth_state_dict(seed=16, use_bias=False, w0=2.0, mod_bias_shift=0.5)
+    m = ModulatedSiren(dim_in=2, dim_hidden=256, dim_out=1, num_layers=5, latent_dim=256, w0=2.0, w0_initial=30.0,
+                       use_bias=False, dropout=p, modulate=True, encoder_type="custom", encoder_path=None,
+                       outer_patch_size=32, inner_patch_size=16, siren_patch_size=24, device=torch.device("cpu"),
+                       activation="sine")
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).train()
+    keep_np = train_keep_mask(3, 5, B * 576, 256, p)
+    under_np, full_np = synth_tiles(81, B), synth_tiles(82, B)
+    out, loss, grads = _iteration(m, torch.from_numpy(under_np).to(DEV), torch.from_numpy(full_np).to(DEV),
+                                  torch.from_numpy(keep_np).to(DEV))
+    want_out, want_loss, want = otrain.train_iteration(sd, torch.from_numpy(under_np), torch.from_numpy(full_np),
+                                                       torch.from_numpy(keep_np), p, w0=2.0)
+    assert float((out.cpu() - want_out).abs().max()) <= 5e-5 and abs(loss - want_loss) <= 1e-5
+    assert set(grads) == set(want) and not any("net.layers" in k and k.endswith("bias") for k in grads)
+    for k, gr in grads.items():
+        err = float((gr - want[k]).abs().max()) / max(float(want[k].abs().max()), 1e-20)
+        assert err <= 1e-3, (k, err)

@@ -56,7 +56,18 @@ constexpr int kThreads = kEpiWarps * 32 + 128;  // + one warpgroup: MMA issuer, 
 // warpgroup shrinks to kRegsOther (per sub-partition: 2 x 232 + 40 <= 512).  At the launch cap of 168 the compiler
 // spilled the tile-walk state, and with 226 KB of shared memory there is next to no L1 left: every reload was an
 // L2 round trip (~300 cycles) on the critical path between phases (tools/timeline.py).
-constexpr int kRegsEpilogue = kEpiWarps == 8 ? 232 : 112, kRegsOther = 40;
+// The pool setmaxnreg redistributes is what the CTA was launched with (threads x launch registers), so
+//   8 epilogue warps: 384 x 168 = 64512 = 256 x 232 + 128 x 40;  16: 640 x 96 = 61440 = 512 x 112 + 128 x 32
+// -- a request beyond the pool never completes (the 16-warp build with 112 / 40 hung for exactly this reason).
+#ifndef MRINR_V5_REGS_EPI
+#define MRINR_V5_REGS_EPI (MRINR_V5_EPI_WARPS == 8 ? 232 : 112)
+#endif
+#ifndef MRINR_V5_REGS_OTHER
+#define MRINR_V5_REGS_OTHER (MRINR_V5_EPI_WARPS == 8 ? 40 : 32)
+#endif
+constexpr int kRegsEpilogue = MRINR_V5_REGS_EPI, kRegsOther = MRINR_V5_REGS_OTHER;
+static_assert(kEpiWarps * 32 * kRegsEpilogue + 128 * kRegsOther <= (kEpiWarps == 8 ? 168 : 96) * kThreads,
+              "setmaxnreg targets exceed the CTA's register pool");
 // Register budget: the register file is split per SM sub-partition (16 384 each) and the 10 (18) warps of the CTA
 // land 3 (5) on some sub-partition, so the cap is 168 (96) registers per thread -- not 65536 / kThreads.
 constexpr int kMaxLayers = 16;

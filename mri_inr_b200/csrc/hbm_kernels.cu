@@ -6,6 +6,7 @@
 // 256-thread CTAs (several waves over 148 SMs at production batch sizes).  Roofline: HBM bandwidth;
 // algorithmic bytes per slice are listed in DESIGN.md.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mrinr {
 
@@ -288,6 +289,108 @@ patches_to_image_fixed_kernel(const float* __restrict__ tiles, const float* __re
     }
     reinterpret_cast<float4*>(out)[n * per_img + rem] = make_float4(__fdiv_rn(acc.x, norm.x), __fdiv_rn(acc.y, norm.y),
                                                                    __fdiv_rn(acc.z, norm.z), __fdiv_rn(acc.w, norm.w));
+  }
+}
+
+// Weighted reassembly as a BAND kernel (I = 16, K = 24: the reference's inner / siren patch sizes).  The gather kernels
+// above keep their loads in registers, and with ~2.25 contributions per output quad a thread cannot hold enough bytes in
+// flight: measured 0.69 of the HBM roofline however the work was cut (profiles/r02_hbm_kernels.txt).  Here a CTA owns one
+// band of one image -- the I output rows yp in [I py, I py + I) of patch row py -- and fetches everything the band needs
+// with bulk-async copies into shared memory before any thread computes: per tile of patch row py its rows 0..I-1 (one
+// contiguous 1536-byte piece) and per tile of patch row py-1 its rows I..K-1 (768 bytes; the overlap zone).  Every tile
+// row is fetched exactly once over the whole grid, nothing waits on registers, and several CTAs per SM keep > 150 KB in
+// flight.  The last band also emits the padq rows below it (rows I..I+padq-1 of its own tiles).  Per output quad the
+// additions run in fold order (py descending, then px descending) and the division is IEEE: bit-identical results.
+// Tile strides in shared memory are padded to 16 mod 32 words so that a quarter-warp's 16-byte reads, which straddle two
+// tiles, fall on distinct banks.
+template <int I, int K>
+struct BandGeom {
+  static constexpr int D = K - I, padq = D / 2, RA = I + padq;
+  static constexpr int strideA = RA * K + (((RA * K) % 32) == 16 ? 0 : (16 - (RA * K) % 32 + 32) % 32);   // words
+  static constexpr int strideB = D * K + (((D * K) % 32) == 16 ? 0 : (16 - (D * K) % 32 + 32) % 32);
+  static_assert(strideA % 4 == 0 && strideB % 4 == 0, "16-byte aligned tiles");
+  static size_t smem_bytes(int nH) { return (size_t)nH * (strideA + strideB) * 4 + 16; }
+};
+
+template <int I, int K, bool HASB>
+__global__ void __launch_bounds__(512)
+patches_to_image_band_kernel(const float* __restrict__ tiles, const float* __restrict__ weights,
+                             const uint8_t* __restrict__ black, long long N, int nV, int nH, float* __restrict__ out) {
+  using G = BandGeom<I, K>;
+  static_assert(K <= 2 * I && I % 4 == 0 && K % 4 == 0 && G::padq % 4 == 0, "at most two patches per axis");
+  constexpr int D = G::D, padq = G::padq, RA = G::RA, KK = K * K, SA = G::strideA, SB = G::strideB;
+  extern __shared__ __align__(128) uint8_t band_smem[];
+  float* sA = reinterpret_cast<float*>(band_smem);            // [nH][RA rows][K] of patch row py
+  float* sB = sA + nH * SA;                                   // [nH][D rows][K]: rows I..K-1 of patch row py-1
+  const uint32_t bar = smem_u32(sB + nH * SB);
+  const int py = blockIdx.x;
+  const bool first = py == 0, lastb = py == nV - 1;
+  const int OW4 = (nH * I) >> 2;
+  const int rr = threadIdx.x / OW4, j = threadIdx.x - rr * OW4;      // row phase 0..3, quad column
+  const int xp = 4 * j + padq;
+  const int px_hi = min(xp / I, nH - 1);
+  const int px_lo = (xp + 3 - K + 1 <= 0) ? 0 : (xp + 3 - K + I) / I;
+  const bool two_x = px_lo < px_hi;
+  const int kx0 = xp - I * px_hi, kx1 = xp - I * px_lo;
+  const int a_hi = px_hi * SA + kx0, a_lo = px_lo * SA + kx1;        // + ky K
+  const int b_hi = px_hi * SB + kx0, b_lo = px_lo * SB + kx1;        // + (ky - I) K
+  const int rowsA = lastb ? RA : I;
+  const uint32_t bytes = (uint32_t)nH * (uint32_t)(rowsA * K * 4 + (first ? 0 : D * K * 4));
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t phase = 0;
+  for (long long n = blockIdx.y; n < N; n += gridDim.y) {
+    const float* rowp = tiles + (size_t)(n * nV + py) * nH * KK;
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0) mbar_expect_tx(bar, bytes);
+      __syncwarp();
+      for (int c = threadIdx.x; c < nH; c += 32) {
+        bulk_g2s(smem_u32(sA + c * SA), rowp + (size_t)c * KK, (uint32_t)(rowsA * K * 4), bar);
+        if (!first) bulk_g2s(smem_u32(sB + c * SB), rowp - (size_t)nH * KK + (size_t)c * KK + I * K, (uint32_t)(D * K * 4), bar);
+      }
+    }
+    bool kA_hi = true, kA_lo = true, kB_hi = true, kB_lo = true;      // keep (= not black)
+    if (HASB) {
+      const uint8_t* bb = black + (n * nV + py) * nH;
+      kA_hi = __ldg(bb + px_hi) == 0;
+      kA_lo = __ldg(bb + px_lo) == 0;
+      if (!first) {
+        kB_hi = __ldg(bb - nH + px_hi) == 0;
+        kB_lo = __ldg(bb - nH + px_lo) == 0;
+      }
+    }
+    mbar_wait(bar, phase, nullptr, 0);
+    phase ^= 1u;
+    const int r_end = lastb ? RA : I;
+    for (int r = rr; r < r_end; r += 4) {
+      if (first && r < padq) continue;                 // above the image
+      const bool two_y = !first && r < D;
+      float4 acc = zero, norm = zero;
+      auto add = [&](const float* sp, bool keep, int ky, int kx) {
+        float4 t = *reinterpret_cast<const float4*>(sp);
+        if (HASB && !keep) t = zero;
+        const float4 w = weights ? __ldg(reinterpret_cast<const float4*>(weights + ky * K + kx)) : one;
+        acc.x = __fadd_rn(acc.x, __fmul_rn(t.x, w.x)); norm.x = __fadd_rn(norm.x, w.x);
+        acc.y = __fadd_rn(acc.y, __fmul_rn(t.y, w.y)); norm.y = __fadd_rn(norm.y, w.y);
+        acc.z = __fadd_rn(acc.z, __fmul_rn(t.z, w.z)); norm.z = __fadd_rn(norm.z, w.z);
+        acc.w = __fadd_rn(acc.w, __fmul_rn(t.w, w.w)); norm.w = __fadd_rn(norm.w, w.w);
+      };
+      add(sA + a_hi + r * K, kA_hi, r, kx0);
+      if (two_x) add(sA + a_lo + r * K, kA_lo, r, kx1);
+      if (two_y) {
+        add(sB + b_hi + r * K, kB_hi, I + r, kx0);
+        if (two_x) add(sB + b_lo + r * K, kB_lo, I + r, kx1);
+      }
+      const int y = I * py + r - padq;
+      reinterpret_cast<float4*>(out)[((size_t)n * (nV * I) + y) * OW4 + j] =
+          make_float4(__fdiv_rn(acc.x, norm.x), __fdiv_rn(acc.y, norm.y), __fdiv_rn(acc.z, norm.z),
+                      __fdiv_rn(acc.w, norm.w));
+    }
+    if (n + gridDim.y < N) __syncthreads();            // the next image's copies overwrite the band
   }
 }
 
@@ -577,6 +680,22 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
       (d_weights == nullptr || aligned16(d_weights))) {
     const long long n_quads = n_pix / 4;
     const long long per_img = n_quads / N;
+    if (I == 16 && K == 24 && nH * I <= 512 && BandGeom<16, 24>::smem_bytes(nH) <= 100 * 1024) {
+      using G = BandGeom<16, 24>;
+      const int smem = (int)G::smem_bytes(nH);
+      const cudaStream_t st = (cudaStream_t)stream;
+      dim3 grid((unsigned)nV, (unsigned)(N < 65535 ? N : 65535));
+      const unsigned threads = (unsigned)(nH * I);          // 4 row phases x (nH I / 4) quads
+      if (d_black) {
+        MRINR_SMEM_OPT_IN((patches_to_image_band_kernel<16, 24, true>), 100 * 1024);
+        patches_to_image_band_kernel<16, 24, true><<<grid, threads, smem, st>>>(d_tiles, d_weights, d_black, N, nV, nH, d_img);
+      } else {
+        MRINR_SMEM_OPT_IN((patches_to_image_band_kernel<16, 24, false>), 100 * 1024);
+        patches_to_image_band_kernel<16, 24, false><<<grid, threads, smem, st>>>(d_tiles, d_weights, d_black, N, nV, nH, d_img);
+      }
+      count_launch();
+      return check_launch("patches_to_image_band");
+    }
     if (I == 16 && (K == 24 || K == 32) && per_img < (1ll << 30)) {
       // a thread walks several images (same pixel position: the window arithmetic and the weights are reused)
       // four images per thread.  (Measured in round 2: fewer, longer-lived CTAs -- ~16 per SM, 44 images per thread,

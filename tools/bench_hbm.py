@@ -46,6 +46,10 @@ rec = torch.empty(N, H, W, device=DEV)
 wts = _weights_on(24, torch.device(DEV))
 report("patches_to_image (weighted, k=24)", timeit(lambda: ops.patches_to_image(tiles, N, (20, 20), 16, weights=wts, out=rec)),
        N * 400 * 2304 + px * 4)
+blk = torch.zeros(N * 400, dtype=torch.uint8, device=DEV)
+blk[::17] = 1
+report("  .. with a black mask (pipeline)", timeit(lambda: ops.patches_to_image(tiles, N, (20, 20), 16, weights=wts, black=blk, out=rec)),
+       N * 400 * 2304 + px * 4 + N * 400)
 report("patches_to_image (unit, k=32)", timeit(lambda: ops.patches_to_image(patches, N, (20, 20), 16, out=rec)),
        N * 400 * 4096 + px * 4)
 report("minmax_normalize (per volume)", timeit(lambda: ops.minmax_normalize(img, groups=max(1, N // 11) if N % 11 == 0 else 1)),

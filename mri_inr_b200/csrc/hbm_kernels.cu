@@ -294,68 +294,115 @@ patches_to_image_fixed_kernel(const float* __restrict__ tiles, const float* __re
 
 // Weighted reassembly as a BAND kernel (I = 16, K = 24: the reference's inner / siren patch sizes).  The gather kernels
 // above keep their loads in registers, and with ~2.25 contributions per output quad a thread cannot hold enough bytes in
-// flight: measured 0.69 of the HBM roofline however the work was cut (profiles/r02_hbm_kernels.txt).  Here a CTA owns one
-// band of one image -- the I output rows yp in [I py, I py + I) of patch row py -- and fetches everything the band needs
-// with bulk-async copies into shared memory before any thread computes: per tile of patch row py its rows 0..I-1 (one
-// contiguous 1536-byte piece) and per tile of patch row py-1 its rows I..K-1 (768 bytes; the overlap zone).  Every tile
-// row is fetched exactly once over the whole grid, nothing waits on registers, and several CTAs per SM keep > 150 KB in
-// flight.  The last band also emits the padq rows below it (rows I..I+padq-1 of its own tiles).  Per output quad the
-// additions run in fold order (py descending, then px descending) and the division is IEEE: bit-identical results.
-// Tile strides in shared memory are padded to 16 mod 32 words so that a quarter-warp's 16-byte reads, which straddle two
-// tiles, fall on distinct banks.
+// flight: measured 0.69 of the HBM roofline however the work was cut (profiles/r02_hbm_kernels.txt).  Here the unit of
+// work is a band -- the I output rows yp in [I py, I py + I) of patch row py of one image -- and a band needs patch row
+// py (rows 0..I-1 of its tiles) and patch row py-1 (rows I..K-1: the overlap zone).  The nH tiles of a patch row are
+// contiguous in memory, so a patch row arrives as ONE bulk-async copy (46 KB) in a shared-memory ring; one CTA per SM
+// walks a contiguous range of (image, py) items, which makes row py-1 the previous item's stage: every tile is fetched
+// exactly once (plus one halo row per CTA), with two rows in flight while a band is computed.  (Cutting the rows into
+// per-tile pieces -- 40 copies of 768 / 1536 bytes per band, conflict-free strides -- ran into the copy engine's issue
+// rate: ~50 ns per copy and SM, 0.53-0.84 of the roofline depending on how many CTAs shared an SM.)  The last band of
+// an image also emits the padq rows below it (rows I..I+padq-1 of its own tiles).
+// A thread keeps its positions -- quad column j, rows rr and rr+8 -- for all bands, so the normaliser F.fold(w) of the
+// interior bands is computed ONCE (additions in fold order: py descending, then px descending) together with its
+// correctly rounded reciprocal.  The quotient acc / norm is then  q0 = acc y;  q1 = q0 + (acc - q0 norm) y;
+// q = q1 + (acc - q1 norm) y  with y = RN(1 / norm) and exact FMA residuals: q1 is a faithful quotient, and one more
+// residual step from a faithful quotient with a correctly rounded reciprocal gives RN(acc / norm) (Markstein) -- the
+// reference's value bit for bit, in 5 instructions instead of the ~12 of a full IEEE division.  The argument needs the
+// residuals to be free of underflow / overflow: quads with an element outside [2^-100, 2^100] (other than an all-zero
+// quad), the first band of an image (no overlap from above) and the extra rows of the last one take __fdiv_rn.
 template <int I, int K>
 struct BandGeom {
   static constexpr int D = K - I, padq = D / 2, RA = I + padq;
-  static constexpr int strideA = RA * K + (((RA * K) % 32) == 16 ? 0 : (16 - (RA * K) % 32 + 32) % 32);   // words
-  static constexpr int strideB = D * K + (((D * K) % 32) == 16 ? 0 : (16 - (D * K) % 32 + 32) % 32);
-  static_assert(strideA % 4 == 0 && strideB % 4 == 0, "16-byte aligned tiles");
-  static size_t smem_bytes(int nH) { return (size_t)nH * (strideA + strideB) * 4 + 16; }
+  static constexpr int kStages = 4;          // rows py-1 and py of the band being computed, two rows in flight
+  static constexpr int kPhases = 8;          // row phases: thread (rr, j) owns rows rr, rr + 8, .. of quad column j
+  static constexpr int kRowsPerThread = I / kPhases;
+  static_assert(I % kPhases == 0 && padq <= kPhases, "row phases");
+  static size_t smem_bytes(int nH) { return (size_t)kStages * nH * K * K * 4 + K * K * 4 + 8 * kStages; }
 };
 
+__device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
+  const float q0 = __fmul_rn(a, y);
+  const float q1 = __fmaf_rn(__fmaf_rn(-q0, b, a), y, q0);
+  return __fmaf_rn(__fmaf_rn(-q1, b, a), y, q1);
+}
+
 template <int I, int K, bool HASB>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(640, 1)
 patches_to_image_band_kernel(const float* __restrict__ tiles, const float* __restrict__ weights,
                              const uint8_t* __restrict__ black, long long N, int nV, int nH, float* __restrict__ out) {
   using G = BandGeom<I, K>;
   static_assert(K <= 2 * I && I % 4 == 0 && K % 4 == 0 && G::padq % 4 == 0, "at most two patches per axis");
-  constexpr int D = G::D, padq = G::padq, RA = G::RA, KK = K * K, SA = G::strideA, SB = G::strideB;
+  constexpr int D = G::D, padq = G::padq, KK = K * K, S = G::kStages, kRows = G::kRowsPerThread;
   extern __shared__ __align__(128) uint8_t band_smem[];
-  float* sA = reinterpret_cast<float*>(band_smem);            // [nH][RA rows][K] of patch row py
-  float* sB = sA + nH * SA;                                   // [nH][D rows][K]: rows I..K-1 of patch row py-1
-  const uint32_t bar = smem_u32(sB + nH * SB);
-  const int py = blockIdx.x;
-  const bool first = py == 0, lastb = py == nV - 1;
+  float* s_data = reinterpret_cast<float*>(band_smem);
+  const int row_words = nH * KK;                       // one patch row: nH tiles, contiguous in global memory too
+  float* s_w = s_data + S * row_words;                 // the K x K weight window (with ~all of the SM's L1 carved out as
+                                                       // shared memory a global read of it is an L2 round trip every time)
+  const uint32_t bar0 = smem_u32(s_w + KK);
+  // this CTA's items t = n nV + py: [t0, t1); its loads start one item earlier when the first band needs the row above
+  const long long T = N * nV;
+  const long long t0 = T * blockIdx.x / gridDim.x, t1 = T * (blockIdx.x + 1) / gridDim.x;
+  if (t0 >= t1) return;
+  const int i_c0 = (t0 % nV) > 0 ? 1 : 0;              // local index of the first computed item
+  const long long tl0 = t0 - i_c0;
+  const int n_items = (int)(t1 - tl0);
+
   const int OW4 = (nH * I) >> 2;
-  const int rr = threadIdx.x / OW4, j = threadIdx.x - rr * OW4;      // row phase 0..3, quad column
+  const int rr = threadIdx.x / OW4, j = threadIdx.x - rr * OW4;      // row phase 0..7, quad column
   const int xp = 4 * j + padq;
   const int px_hi = min(xp / I, nH - 1);
   const int px_lo = (xp + 3 - K + 1 <= 0) ? 0 : (xp + 3 - K + I) / I;
   const bool two_x = px_lo < px_hi;
   const int kx0 = xp - I * px_hi, kx1 = xp - I * px_lo;
-  const int a_hi = px_hi * SA + kx0, a_lo = px_lo * SA + kx1;        // + ky K
-  const int b_hi = px_hi * SB + kx0, b_lo = px_lo * SB + kx1;        // + (ky - I) K
-  const int rowsA = lastb ? RA : I;
-  const uint32_t bytes = (uint32_t)nH * (uint32_t)(rowsA * K * 4 + (first ? 0 : D * K * 4));
+  const int o_hi = px_hi * KK + kx0, o_lo = px_lo * KK + kx1;        // + ky K, within a patch row
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    for (int s = 0; s < S; ++s) mbar_init(bar0 + 8u * s, 1);
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < KK; i += blockDim.x) s_w[i] = weights ? __ldg(weights + i) : 1.f;
   __syncthreads();
-  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t phase = 0;
-  for (long long n = blockIdx.y; n < N; n += gridDim.y) {
-    const float* rowp = tiles + (size_t)(n * nV + py) * nH * KK;
-    if (threadIdx.x < 32) {
-      if (threadIdx.x == 0) mbar_expect_tx(bar, bytes);
-      __syncwarp();
-      for (int c = threadIdx.x; c < nH; c += 32) {
-        bulk_g2s(smem_u32(sA + c * SA), rowp + (size_t)c * KK, (uint32_t)(rowsA * K * 4), bar);
-        if (!first) bulk_g2s(smem_u32(sB + c * SB), rowp - (size_t)nH * KK + (size_t)c * KK + I * K, (uint32_t)(D * K * 4), bar);
-      }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto weight = [&](int ky, int kx) -> float4 { return *reinterpret_cast<const float4*>(s_w + ky * K + kx); };
+  auto fetch = [&](int i) {          // patch row of item tl0 + i -> stage i % S (one thread)
+    const uint32_t bar = bar0 + 8u * (uint32_t)(i % S);
+    mbar_expect_tx(bar, (uint32_t)row_words * 4u);
+    bulk_g2s(smem_u32(s_data + (i % S) * row_words), tiles + (size_t)(tl0 + i) * row_words, (uint32_t)row_words * 4u, bar);
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < i_c0 + 2 && i < n_items; ++i) fetch(i);
+
+  // ---- per-position constants of an interior band (py > 0, rows < I), while the first rows are on their way ----
+  float4 nrm[kRows], rcp[kRows];
+  bool exact_ok = true;              // the reciprocal path's range argument holds for this thread's normalisers
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    const int r = rr + G::kPhases * k;
+    float4 nm = zero;
+    auto addw = [&](const float4& w) {
+      nm.x = __fadd_rn(nm.x, w.x); nm.y = __fadd_rn(nm.y, w.y); nm.z = __fadd_rn(nm.z, w.z); nm.w = __fadd_rn(nm.w, w.w);
+    };
+    addw(weight(r, kx0));
+    if (two_x) addw(weight(r, kx1));
+    if (r < D) {
+      addw(weight(I + r, kx0));
+      if (two_x) addw(weight(I + r, kx1));
     }
+    nrm[k] = nm;
+    rcp[k] = make_float4(__frcp_rn(nm.x), __frcp_rn(nm.y), __frcp_rn(nm.z), __frcp_rn(nm.w));
+    const float lo = fminf(fminf(nm.x, nm.y), fminf(nm.z, nm.w)), hi = fmaxf(fmaxf(nm.x, nm.y), fmaxf(nm.z, nm.w));
+    exact_ok = exact_ok && lo >= 0x1p-20f && hi <= 0x1p20f;       // (false for NaN as well)
+  }
+
+  if (i_c0 == 1) mbar_wait(bar0, 0u, nullptr, 0);       // the halo row (it is nobody's "current" row)
+  for (int i = i_c0; i < n_items; ++i) {
+    if (threadIdx.x == 0 && i + 2 < n_items) fetch(i + 2);       // into the stage of item i-2: released by the barrier below
+    const long long t = tl0 + i;
+    const int py = (int)(t % nV);
+    const bool first = py == 0, lastb = py == nV - 1;
     bool kA_hi = true, kA_lo = true, kB_hi = true, kB_lo = true;      // keep (= not black)
     if (HASB) {
-      const uint8_t* bb = black + (n * nV + py) * nH;
+      const uint8_t* bb = black + t * nH;
       kA_hi = __ldg(bb + px_hi) == 0;
       kA_lo = __ldg(bb + px_lo) == 0;
       if (!first) {
@@ -363,34 +410,56 @@ patches_to_image_band_kernel(const float* __restrict__ tiles, const float* __res
         kB_lo = __ldg(bb - nH + px_lo) == 0;
       }
     }
-    mbar_wait(bar, phase, nullptr, 0);
-    phase ^= 1u;
-    const int r_end = lastb ? RA : I;
-    for (int r = rr; r < r_end; r += 4) {
-      if (first && r < padq) continue;                 // above the image
-      const bool two_y = !first && r < D;
-      float4 acc = zero, norm = zero;
+    mbar_wait(bar0 + 8u * (uint32_t)(i % S), (uint32_t)(i / S) & 1u, nullptr, 0);
+    const float* sA = s_data + (i % S) * row_words;
+    const float* sB = s_data + ((i + S - 1) % S) * row_words;
+    float4* orow = reinterpret_cast<float4*>(out) + (t * I - padq) * (long long)OW4 + j;      // + r OW4 (r >= padq when t = 0)
+    // one output quad: row r of the band; hoisted = index into nrm / rcp, or -1 for the on-the-fly path
+    auto emit = [&](int r, bool two_y, int hoisted) {
+      float4 acc = zero, nm = zero;
       auto add = [&](const float* sp, bool keep, int ky, int kx) {
-        float4 t = *reinterpret_cast<const float4*>(sp);
-        if (HASB && !keep) t = zero;
-        const float4 w = weights ? __ldg(reinterpret_cast<const float4*>(weights + ky * K + kx)) : one;
-        acc.x = __fadd_rn(acc.x, __fmul_rn(t.x, w.x)); norm.x = __fadd_rn(norm.x, w.x);
-        acc.y = __fadd_rn(acc.y, __fmul_rn(t.y, w.y)); norm.y = __fadd_rn(norm.y, w.y);
-        acc.z = __fadd_rn(acc.z, __fmul_rn(t.z, w.z)); norm.z = __fadd_rn(norm.z, w.z);
-        acc.w = __fadd_rn(acc.w, __fmul_rn(t.w, w.w)); norm.w = __fadd_rn(norm.w, w.w);
+        float4 tv = *reinterpret_cast<const float4*>(sp);
+        if (HASB && !keep) tv = zero;
+        const float4 w = weight(ky, kx);
+        acc.x = __fadd_rn(acc.x, __fmul_rn(tv.x, w.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(tv.y, w.y));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(tv.z, w.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(tv.w, w.w));
+        if (hoisted < 0) {
+          nm.x = __fadd_rn(nm.x, w.x); nm.y = __fadd_rn(nm.y, w.y); nm.z = __fadd_rn(nm.z, w.z); nm.w = __fadd_rn(nm.w, w.w);
+        }
       };
-      add(sA + a_hi + r * K, kA_hi, r, kx0);
-      if (two_x) add(sA + a_lo + r * K, kA_lo, r, kx1);
+      add(sA + o_hi + r * K, kA_hi, r, kx0);
+      if (two_x) add(sA + o_lo + r * K, kA_lo, r, kx1);
       if (two_y) {
-        add(sB + b_hi + r * K, kB_hi, I + r, kx0);
-        if (two_x) add(sB + b_lo + r * K, kB_lo, I + r, kx1);
+        add(sB + o_hi + (I + r) * K, kB_hi, I + r, kx0);
+        if (two_x) add(sB + o_lo + (I + r) * K, kB_lo, I + r, kx1);
       }
-      const int y = I * py + r - padq;
-      reinterpret_cast<float4*>(out)[((size_t)n * (nV * I) + y) * OW4 + j] =
-          make_float4(__fdiv_rn(acc.x, norm.x), __fdiv_rn(acc.y, norm.y), __fdiv_rn(acc.z, norm.z),
-                      __fdiv_rn(acc.w, norm.w));
+      float4 q;
+      bool fast = false;
+      if (hoisted >= 0) {
+        const float ax = fabsf(acc.x), ay = fabsf(acc.y), az = fabsf(acc.z), aw = fabsf(acc.w);
+        const float hi = fmaxf(fmaxf(ax, ay), fmaxf(az, aw)), lo = fminf(fminf(ax, ay), fminf(az, aw));
+        fast = exact_ok && hi <= 0x1p100f && (lo >= 0x1p-100f || hi == 0.f);
+        nm = nrm[hoisted];
+      }
+      if (fast) {
+        const float4 y = rcp[hoisted];
+        q = make_float4(div_by_rcp(acc.x, nm.x, y.x), div_by_rcp(acc.y, nm.y, y.y), div_by_rcp(acc.z, nm.z, y.z),
+                        div_by_rcp(acc.w, nm.w, y.w));
+      } else {
+        q = make_float4(__fdiv_rn(acc.x, nm.x), __fdiv_rn(acc.y, nm.y), __fdiv_rn(acc.z, nm.z), __fdiv_rn(acc.w, nm.w));
+      }
+      orow[(long long)r * OW4] = q;
+    };
+    if (!first) {
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) emit(rr + G::kPhases * k, rr + G::kPhases * k < D, k);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < kRows; ++k)
+        if (rr + G::kPhases * k >= padq) emit(rr + G::kPhases * k, false, -1);       // rows above the image do not exist
     }
-    if (n + gridDim.y < N) __syncthreads();            // the next image's copies overwrite the band
+    if (lastb && rr < padq) emit(I + rr, false, -1);
+    __syncthreads();            // every thread is done with rows i-1 and i: the next fetch may overwrite row i-1's stage
   }
 }
 
@@ -680,17 +749,25 @@ extern "C" int mrinr_patches_to_image(const float* d_tiles, const float* d_weigh
       (d_weights == nullptr || aligned16(d_weights))) {
     const long long n_quads = n_pix / 4;
     const long long per_img = n_quads / N;
-    if (I == 16 && K == 24 && nH * I <= 512 && BandGeom<16, 24>::smem_bytes(nH) <= 100 * 1024) {
+    if (I == 16 && K == 24 && nH * I <= 320 && BandGeom<16, 24>::smem_bytes(nH) <= 227 * 1024) {
       using G = BandGeom<16, 24>;
       const int smem = (int)G::smem_bytes(nH);
       const cudaStream_t st = (cudaStream_t)stream;
-      dim3 grid((unsigned)nV, (unsigned)(N < 65535 ? N : 65535));
-      const unsigned threads = (unsigned)(nH * I);          // 4 row phases x (nH I / 4) quads
+      // persistent: one CTA per SM, each walks a contiguous range of (image, patch row) items
+      int sms = 148;
+      {
+        int dev = 0;
+        MRINR_CUDA(cudaGetDevice(&dev));
+        MRINR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      }
+      const long long items = (long long)N * nV;
+      dim3 grid((unsigned)(items < sms ? items : sms));
+      const unsigned threads = (unsigned)(G::kPhases * nH * I / 4);          // 8 row phases x (nH I / 4) quads
       if (d_black) {
-        MRINR_SMEM_OPT_IN((patches_to_image_band_kernel<16, 24, true>), 100 * 1024);
+        MRINR_SMEM_OPT_IN((patches_to_image_band_kernel<16, 24, true>), 227 * 1024);
         patches_to_image_band_kernel<16, 24, true><<<grid, threads, smem, st>>>(d_tiles, d_weights, d_black, N, nV, nH, d_img);
       } else {
-        MRINR_SMEM_OPT_IN((patches_to_image_band_kernel<16, 24, false>), 100 * 1024);
+        MRINR_SMEM_OPT_IN((patches_to_image_band_kernel<16, 24, false>), 227 * 1024);
         patches_to_image_band_kernel<16, 24, false><<<grid, threads, smem, st>>>(d_tiles, d_weights, d_black, N, nV, nH, d_img);
       }
       count_launch();

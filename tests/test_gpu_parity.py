@@ -70,6 +70,44 @@ def test_tiling_bit_exact(golden, tag, hw):
     assert np.array_equal(plain.cpu().numpy().view(np.uint32), g[f"{tag}_plain"].view(np.uint32))
 
 
+def _same_bits(got, want, what):
+    bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+    assert len(bad) == 0, (f"{what}: {len(bad)} of {got.size} elements differ; first: " +
+                           "; ".join(f"[{y},{x}] got {got[y, x]!r} want {want[y, x]!r}" for y, x in bad[:6]))
+
+
+@pytest.mark.parametrize("nv,nh,n_img", [(20, 20, 37), (3, 5, 9), (1, 1, 4), (2, 20, 700)])
+def test_weighted_reassembly_bit_exact_over_the_float_range(nv, nh, n_img):
+    """The band kernel (csrc/hbm_kernels.cu) divides by a hoisted, correctly rounded reciprocal with two exact residual
+    steps and falls back to an IEEE division outside [2^-100, 2^100]: F.fold(x w) / F.fold(w) of the reference
+    (tiling.py:91-140) bit for bit, for values spread over the whole fp32 range, zeros, black patches, more images
+    than CTAs walk in one pass (700) and degenerate grids."""
+    from mri_inr_b200 import ops
+    from mri_inr_b200.tiling import _weights_on
+
+    rs = np.random.RandomState(nv * 100 + nh)
+    P = n_img * nv * nh
+    tiles = rs.uniform(-1, 1, size=(P, 24, 24)).astype(np.float32)
+    n_wide = min(P, 4000)                          # a subset gets per-element scales over the float range
+    tiles[:n_wide] *= np.exp2(rs.randint(-140, 100, size=(n_wide, 24, 24))).astype(np.float32)
+    tiles[rs.rand(P) < 0.05] = 0.0
+    tiles[rs.rand(P, 24, 24) < 0.02] = 0.0
+    black = rs.rand(P) < 0.1
+    t = torch.from_numpy(tiles).to(DEV)
+    w = _weights_on(24, torch.device(DEV))
+    got = ops.patches_to_image(t, n_img, (nv, nh), 16, weights=w).cpu().numpy()
+    got_b = ops.patches_to_image(t, n_img, (nv, nh), 16, weights=w, black=torch.from_numpy(black.astype(np.uint8)).to(DEV)).cpu().numpy()
+    zt = tiles.copy()
+    zt[black] = 0.0
+    check = range(n_img) if n_img <= 40 else list(range(0, n_img, 53)) + [n_img - 1]
+    for i in check:
+        sl = slice(i * nv * nh, (i + 1) * nv * nh)
+        want = otiling.patches_to_image_weighted_average(tiles[sl], [(nv, nh)], 24, 16)[0]
+        _same_bits(got[i], want, f"image {i}")
+        want_b = otiling.patches_to_image_weighted_average(zt[sl], [(nv, nh)], 24, 16)[0]
+        _same_bits(got_b[i], want_b, f"image {i} (black mask)")
+
+
 def test_weight_matrix_bit_exact(golden):
     from mri_inr_b200 import tiling
 

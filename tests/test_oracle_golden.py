@@ -82,9 +82,9 @@ def test_tiling_matches_reference(golden, tag, hw):
     wavg = tiling.patches_to_image_weighted_average(reint, info, 24, 16)
     plain = tiling.patches_to_image(patches, info, 32, 16)
     assert wavg.shape == g[f"{tag}_wavg"].shape
-    # identical accumulation order is not guaranteed for the numpy restatement: compare to 1 ulp-ish
-    np.testing.assert_allclose(wavg, g[f"{tag}_wavg"], rtol=0, atol=3e-7)
-    np.testing.assert_allclose(plain, g[f"{tag}_plain"], rtol=0, atol=3e-7)
+    # the restatement accumulates in F.fold's order (decreasing patch row, then column): bit-identical to the reference
+    assert np.array_equal(wavg.view(np.uint32), g[f"{tag}_wavg"].view(np.uint32))
+    assert np.array_equal(plain.view(np.uint32), g[f"{tag}_plain"].view(np.uint32))
 
 
 def test_normalize_scan(golden):

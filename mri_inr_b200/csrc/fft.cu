@@ -4,7 +4,8 @@
 // package is an un-vendored dependency of the reference, requirements.txt:1 -- parity against it is UNPINNED and is
 // anchored on torch.fft instead, tests/test_gpu_parity.py::test_kspace_front_end).
 //
-// Hand-written mixed-radix (2, 3, 4, 5) Stockham FFT in shared memory, two HBM passes per image:
+// Hand-written FFT, two HBM passes per image; length 320 (the reference's slices) runs register-resident as 16 x 20
+// (fft320.cuh, below), any other product of 2, 3 and 5 as a mixed-radix (2, 3, 4, 5) Stockham FFT in shared memory:
 //   pass 1 (rows):    k-space [N,H,W] complex -> mask x ifftshift folded into the load index -> W-point transform of
 //                     8 rows per CTA -> fftshift folded into the store index -> workspace [N,H,W] complex
 //   pass 2 (columns): 8 adjacent columns per CTA (64-byte row segments), H-point transform, shift on store, and either
@@ -13,6 +14,7 @@
 // The twiddle table exp(+-2 pi i j / n) is built per CTA with sincospif (exact argument reduction), so the
 // transform is accurate to a few fp32 ulps of the largest element.
 #include "common.cuh"
+#include "fft320.cuh"
 
 namespace mrinr {
 namespace fft {
@@ -243,6 +245,126 @@ cols_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __
   }
 }
 
+// ---- length 320 (the reference's knee slices): register-resident transform, fft320.cuh ----
+// 320 = 16 x 20: a thread takes the 16 inputs x'[20 n1 + n2] of one residue n2 straight from global memory (the
+// ifftshift is a permutation of n1), does a 16-point DFT in registers, multiplies by w320^(n2 k1) (table in shared
+// memory, orthonormal scale folded in) and hands the values over through shared memory ONCE; a thread then takes the 20
+// values of one k1, does a 20-point prime-factor DFT in registers and stores X[k1 + 16 k2] (the fftshift is a
+// permutation of k2).  ~40 instructions per point instead of ~129 for the four shared-memory Stockham passes above
+// (profiles/r02_metrics_fft_ncu.txt): the passes become HBM-bound.
+constexpr int kSeq320 = 16;          // sequences (rows / adjacent columns) per CTA
+constexpr int kThreads320 = 20 * kSeq320;
+
+template <bool INV>
+__device__ __forceinline__ void build_twiddles320(float2* tw, float scale) {
+  for (int i = threadIdx.x; i < 320; i += kThreads320) {
+    float sn, cs;
+    sincospif(2.0f * (float)i / 320.0f, &sn, &cs);
+    tw[i] = make_float2(cs * scale, (INV ? sn : -sn) * scale);
+  }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(kThreads320)
+rows320_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmask, float2* __restrict__ out, long long n_rows,
+               float scale) {
+  using namespace fft320;
+  __shared__ float2 tw[320];
+  __shared__ float2 ys[kSeq320][20 * 17];          // [row][n2 * 17 + k1]: odd stride, conflict-free both ways
+  build_twiddles320<INV>(tw, scale);
+  const long long row0 = (long long)blockIdx.x * kSeq320;
+  {
+    const int r = threadIdx.x / 20, t = threadIdx.x - 20 * r;
+    const long long row = row0 + r;
+    C a[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const int i = src_index(n1, t);
+      float2 v = make_float2(0.f, 0.f);
+      if (row < n_rows) {
+        v = __ldg(in + row * 320 + i);
+        if (colmask && !colmask[i]) v = make_float2(0.f, 0.f);
+      }
+      a[n1] = mk(v.x, v.y);
+    }
+    dft16<INV>(a);
+    __syncthreads();                                // twiddle table complete
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const float2 w = tw[twiddle_index(t, k1)];
+      const C y = mulc(a[k1], w.x, w.y);            // (k1 = 0: w = scale)
+      ys[r][t * 17 + k1] = make_float2(y.x, y.y);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 * kSeq320) {
+    const int r = threadIdx.x >> 4, k1 = threadIdx.x & 15;
+    const long long row = row0 + r;
+    C b[20];
+#pragma unroll
+    for (int n2 = 0; n2 < 20; ++n2) {
+      const float2 v = ys[r][n2 * 17 + k1];
+      b[n2] = mk(v.x, v.y);
+    }
+    dft20<INV>(b);
+    if (row < n_rows) {
+#pragma unroll
+      for (int k2 = 0; k2 < 20; ++k2) out[row * 320 + dst_index(k1, k2)] = make_float2(b[k2].x, b[k2].y);
+    }
+  }
+}
+
+// columns of [N, 320, W]: 16 adjacent columns per CTA (128-byte row segments), complex or magnitude output
+template <bool INV, bool ABS>
+__global__ void __launch_bounds__(kThreads320)
+cols320_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __restrict__ out_abs, int W, float scale) {
+  using namespace fft320;
+  __shared__ float2 tw[320];
+  __shared__ float2 ys[320 * kSeq320];             // [(n2 * 16 + k1) * 16 + g]
+  build_twiddles320<INV>(tw, scale);
+  const long long img = blockIdx.y;
+  const int x0 = blockIdx.x * kSeq320;
+  const float2* src = in + img * 320ll * W;
+  {
+    const int g = threadIdx.x & (kSeq320 - 1), n2 = threadIdx.x / kSeq320;
+    const bool live = x0 + g < W;
+    C a[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      float2 v = make_float2(0.f, 0.f);
+      if (live) v = __ldg(src + (long long)src_index(n1, n2) * W + x0 + g);
+      a[n1] = mk(v.x, v.y);
+    }
+    dft16<INV>(a);
+    __syncthreads();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const float2 w = tw[twiddle_index(n2, k1)];
+      const C y = mulc(a[k1], w.x, w.y);
+      ys[(n2 * 16 + k1) * kSeq320 + g] = make_float2(y.x, y.y);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 * kSeq320) {
+    const int g = threadIdx.x & (kSeq320 - 1), k1 = threadIdx.x / kSeq320;
+    C b[20];
+#pragma unroll
+    for (int n2 = 0; n2 < 20; ++n2) {
+      const float2 v = ys[(n2 * 16 + k1) * kSeq320 + g];
+      b[n2] = mk(v.x, v.y);
+    }
+    dft20<INV>(b);
+    if (x0 + g < W) {
+#pragma unroll
+      for (int k2 = 0; k2 < 20; ++k2) {
+        const long long dst = img * 320ll * W + (long long)dst_index(k1, k2) * W + x0 + g;
+        if (ABS) out_abs[dst] = sqrtf(__fadd_rn(__fmul_rn(b[k2].x, b[k2].x), __fmul_rn(b[k2].y, b[k2].y)));   // fastmri.complex_abs
+        else out_c[dst] = make_float2(b[k2].x, b[k2].y);
+      }
+    }
+  }
+}
+
 static bool make_plan(int n, Plan* p) {
   if (n < 2 || n > kMaxN) return false;
   p->n = n;
@@ -292,8 +414,22 @@ static int run(const float* d_in, const uint8_t* d_colmask, long long N, int H, 
                                                                sgn, sh);                                    \
     }                                                                                                       \
   } while (0)
-  if (W == 320) MRINR_FFT_ROWS(320); else if (W == 256) MRINR_FFT_ROWS(256); else MRINR_FFT_ROWS(0);
-  if (H == 320) MRINR_FFT_COLS(320); else if (H == 256) MRINR_FFT_COLS(256); else MRINR_FFT_COLS(0);
+  if (W == 320) {
+    const unsigned g320 = (unsigned)((n_rows + kSeq320 - 1) / kSeq320);
+    if (inverse) rows320_kernel<true><<<g320, kThreads320, 0, st>>>(in2, d_colmask, tmp, n_rows, sw);
+    else rows320_kernel<false><<<g320, kThreads320, 0, st>>>(in2, d_colmask, tmp, n_rows, sw);
+  } else if (W == 256) MRINR_FFT_ROWS(256); else MRINR_FFT_ROWS(0);
+  if (H == 320) {
+    const dim3 g320((W + kSeq320 - 1) / kSeq320, (unsigned)N);
+    float2* oc = reinterpret_cast<float2*>(d_out_c);
+    if (d_out_abs) {
+      if (inverse) cols320_kernel<true, true><<<g320, kThreads320, 0, st>>>(tmp, nullptr, d_out_abs, W, sh);
+      else cols320_kernel<false, true><<<g320, kThreads320, 0, st>>>(tmp, nullptr, d_out_abs, W, sh);
+    } else {
+      if (inverse) cols320_kernel<true, false><<<g320, kThreads320, 0, st>>>(tmp, oc, nullptr, W, sh);
+      else cols320_kernel<false, false><<<g320, kThreads320, 0, st>>>(tmp, oc, nullptr, W, sh);
+    }
+  } else if (H == 256) MRINR_FFT_COLS(256); else MRINR_FFT_COLS(0);
 #undef MRINR_FFT_ROWS
 #undef MRINR_FFT_COLS
   count_launch(2);

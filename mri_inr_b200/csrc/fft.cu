@@ -255,11 +255,14 @@ cols_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float* __
 constexpr int kSeq320 = 16;          // sequences (rows / adjacent columns) per CTA
 constexpr int kThreads320 = 20 * kSeq320;
 
+// tw[k1 * 20 + n2] = scale * w320^(n2 k1): indexed by the consumer's (k1, n2), so that the 20 threads of a row read 20
+// consecutive entries (a table indexed by the exponent n2 k1 is read with stride k1: up to 20-way bank conflicts)
 template <bool INV>
 __device__ __forceinline__ void build_twiddles320(float2* tw, float scale) {
   for (int i = threadIdx.x; i < 320; i += kThreads320) {
+    const int k1 = i / 20, n2 = i - 20 * k1;
     float sn, cs;
-    sincospif(2.0f * (float)i / 320.0f, &sn, &cs);
+    sincospif(2.0f * (float)fft320::twiddle_index(n2, k1) / 320.0f, &sn, &cs);
     tw[i] = make_float2(cs * scale, (INV ? sn : -sn) * scale);
   }
 }
@@ -276,22 +279,25 @@ rows320_kernel(const float2* __restrict__ in, const uint8_t* __restrict__ colmas
   {
     const int r = threadIdx.x / 20, t = threadIdx.x - 20 * r;
     const long long row = row0 + r;
-    C a[16];
+    // all 16 loads first, then the mask: written as one loop the compiler chained load -> mask -> select per value,
+    // i.e. 16 dependent DRAM round trips per thread (ncu: 63 % long-scoreboard stalls, 23 % issue, 0.64 ms)
+    float2 raw[16];
+    uint8_t keep[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-      const int i = src_index(n1, t);
-      float2 v = make_float2(0.f, 0.f);
-      if (row < n_rows) {
-        v = __ldg(in + row * 320 + i);
-        if (colmask && !colmask[i]) v = make_float2(0.f, 0.f);
-      }
-      a[n1] = mk(v.x, v.y);
+      raw[n1] = make_float2(0.f, 0.f);
+      if (row < n_rows) raw[n1] = __ldg(in + row * 320 + src_index(n1, t));
     }
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) keep[n1] = colmask ? __ldg(colmask + src_index(n1, t)) : (uint8_t)1;
+    C a[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) a[n1] = keep[n1] ? mk(raw[n1].x, raw[n1].y) : mk(0.f, 0.f);
     dft16<INV>(a);
     __syncthreads();                                // twiddle table complete
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
-      const float2 w = tw[twiddle_index(t, k1)];
+      const float2 w = tw[k1 * 20 + t];
       const C y = mulc(a[k1], w.x, w.y);            // (k1 = 0: w = scale)
       ys[r][t * 17 + k1] = make_float2(y.x, y.y);
     }
@@ -339,7 +345,7 @@ cols320_kernel(const float2* __restrict__ in, float2* __restrict__ out_c, float*
     __syncthreads();
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
-      const float2 w = tw[twiddle_index(n2, k1)];
+      const float2 w = tw[k1 * 20 + n2];
       const C y = mulc(a[k1], w.x, w.y);
       ys[(n2 * 16 + k1) * kSeq320 + g] = make_float2(y.x, y.y);
     }

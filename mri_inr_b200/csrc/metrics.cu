@@ -44,27 +44,34 @@ reduce_kernel(const float* __restrict__ orig, const float* __restrict__ pred, lo
   double sse = 0.0, so2 = 0.0, so = 0.0, sp = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   if ((n & 3) == 0 && aligned16(o) && aligned16(p)) {
-    // 16-byte loads, two in flight per image; fp32 partial sums over 8 values, fp64 across them
+    // 16-byte loads, kU per image in flight per thread (all issued before the first use); fp32 partial sums over
+    // 4 kU values, fp64 across them.  A thread makes several trips: the block reduction and the six atomics at the
+    // end are paid once per ~100 loads, not once per 4.
+    constexpr int kU = 4;
     const float4* o4 = reinterpret_cast<const float4*>(o);
     const float4* p4 = reinterpret_cast<const float4*>(p);
     const long long n4 = n >> 2;
-    auto eat = [&](const float4& a, const float4& b, float& e, float& q, float& sa, float& sb) {
-      mn = fminf(mn, fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w))));
-      mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
-      const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
-      e = fmaf(d0, d0, e); e = fmaf(d1, d1, e); e = fmaf(d2, d2, e); e = fmaf(d3, d3, e);
-      q = fmaf(a.x, a.x, q); q = fmaf(a.y, a.y, q); q = fmaf(a.z, a.z, q); q = fmaf(a.w, a.w, q);
-      sa += (a.x + a.y) + (a.z + a.w);
-      sb += (b.x + b.y) + (b.z + b.w);
-    };
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
-      const bool two = i + stride < n4;
-      const float4 a0 = __ldg(o4 + i), b0 = __ldg(p4 + i);
-      float4 a1 = a0, b1 = b0;
-      if (two) { a1 = __ldg(o4 + i + stride); b1 = __ldg(p4 + i + stride); }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += kU * stride) {
+      float4 a[kU], b[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const long long j = i + k * stride < n4 ? i + k * stride : i;        // the tail repeats element i: skipped below
+        a[k] = __ldg(o4 + j);
+        b[k] = __ldg(p4 + j);
+      }
       float e = 0.f, q = 0.f, sa = 0.f, sb = 0.f;
-      eat(a0, b0, e, q, sa, sb);
-      if (two) eat(a1, b1, e, q, sa, sb);
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        if (k > 0 && i + k * stride >= n4) break;
+        const float4 x = a[k], y = b[k];
+        mn = fminf(mn, fminf(fminf(fminf(x.x, x.y), fminf(x.z, x.w)), fminf(fminf(y.x, y.y), fminf(y.z, y.w))));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)), fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w))));
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        e = fmaf(d0, d0, e); e = fmaf(d1, d1, e); e = fmaf(d2, d2, e); e = fmaf(d3, d3, e);
+        q = fmaf(x.x, x.x, q); q = fmaf(x.y, x.y, q); q = fmaf(x.z, x.z, q); q = fmaf(x.w, x.w, q);
+        sa += (x.x + x.y) + (x.z + x.w);
+        sb += (y.x + y.y) + (y.z + y.w);
+      }
       sse += (double)e; so2 += (double)q; so += (double)sa; sp += (double)sb;
     }
   } else {
@@ -186,111 +193,175 @@ ssim_kernel(const float* __restrict__ orig, const float* __restrict__ pred, int 
   }
 }
 
-// SSIM as a row-streaming kernel (W a multiple of 4, 16-byte aligned images).  A warp owns 120 window columns of a
-// row segment of one image pair: lane l carries the four pixel columns 120 b + 4 l .. + 3 (lanes 30 and 31 only supply
-// the 8 halo columns) and walks down the rows keeping the VERTICAL 7-row sums of x, y, xx, yy, xy of its columns in
-// registers (x, y, xx + yy, xy: four quantities) -- the row entering the window is added, the row leaving it is read again (L1) and subtracted -- and for
-// every row combines them HORIZONTALLY with the two neighbouring lanes' sums (6 shuffles per quantity, 13 additions
-// without cancellation for the four 7-column windows).  ~60 instructions per window instead of ~170 for the tiled
-// kernel below, no shared memory, no barriers.  Both images are centred by their means (pass 1) before squaring, so
-// E[x^2] - E[x]^2 is formed from numbers of the size of the contrast; the running sums restart with every row segment.
+// SSIM as a row-streaming kernel (W a multiple of 4, 16-byte aligned images).  A CTA walks row segments of image
+// pairs, a warp owns 120 window columns of them: lane l carries the four pixel columns 120 cb + 4 l .. + 3 (lanes 30 and
+// 31 only supply the 8 halo columns) and walks down the rows keeping the VERTICAL 7-row sums of its columns in
+// registers, then combines them HORIZONTALLY with the two neighbouring lanes' prefix sums (4 shuffles per quantity, 11
+// additions without cancellation for the four 7-column windows).  No shared memory, no barriers; every loop bound is
+// CTA-uniform (blockIdx only), so the shuffles sit in provably convergent code (the first version derived the row
+// range from the warp index: ptxas wrapped all 24 shuffles of an iteration in WARPSYNC / collective bookkeeping).
+//
+// Arithmetic, per pixel column, with u = x - mean(x), v = y - mean(y) (image means from pass 1: E[x^2] - E[x]^2 is
+// then formed from numbers of the size of the contrast) and "n" / "o" the rows entering / leaving the window:
+//   d = n - o, s = u_n + u_o = (n + o) - 2 mean:   sum u += dx,   sum (u^2 + v^2) += dx sx + dy sy,
+//                                                   sum 2uv += dx sy + sx dy         (u_n v_n - u_o v_o, twice)
+// -- 12 operations per column PAIR as packed fp32x2 (a float4 load is two pairs), no separate "subtract the old row"
+// pass: during the first 7 rows of a segment the leaving row is the constant (mean x, mean y), i.e. u = v = 0.
+// Window formula with the divisions by 49 / 48 cancelled between numerator and denominator (S = 7x7 sums):
+//   Ux = Sx + 49 mean x, C1 = 49^2 c1, C2 = 48 c2:
+//   ssim = (2 Ux Uy + C1)(S2uv - (2/49) Sx Sy + C2) / ((Ux^2 + Uy^2 + C1)(Suu+vv - (Sx^2 + Sy^2)/49 + C2))
+// also packed over window pairs.  ~55 instructions per window (first streaming version: 100; tiled kernel: 170).
 constexpr int kColsPerWarp = 120;
-__global__ void __launch_bounds__(128)
+constexpr int kStreamMaxWarps = 4;
+
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+__global__ void __launch_bounds__(32 * kStreamMaxWarps, 6)
 ssim_stream_kernel(const float* __restrict__ orig, const float* __restrict__ pred, int H, int W, int n_colblocks,
-                   int n_seg, int rows_per_seg, Acc* __restrict__ acc) {
+                   int cb_groups, long long N, Acc* __restrict__ acc) {
   const int lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (segment, column block) of this warp
-  if (unit >= n_colblocks * n_seg) return;
-  const int seg = unit / n_colblocks, cb = unit - seg * n_colblocks;
-  const long long g = blockIdx.y;
+  const int nx = W - kWin + 1, ny = H - kWin + 1;
+  // Work = cb_groups x N x ny window rows, cut into gridDim.x equal contiguous ranges (CTA-uniform bounds): every CTA
+  // gets the same number of rows whatever N is (with one (pair, segment) per CTA, 2 112 CTAs on 1 036 slots ran as two
+  // full waves and a nearly empty third).  A range restarts the running sums where it begins and at every image boundary.
+  const long long rows_all = (long long)cb_groups * N * ny;
+  long long r = rows_all * blockIdx.x / gridDim.x;
+  const long long r_end = rows_all * (blockIdx.x + 1) / gridDim.x;
+  while (r < r_end) {
+  const int grp = (int)(r / (N * ny));
+  const long long rg = r - (long long)grp * N * ny;
+  const long long g = rg / ny;
+  const int y_a = (int)(rg - g * ny);
+  const int y_b = (int)min((long long)ny, y_a + (r_end - r));               // window rows [y_a, y_b) of pair g
+  r += y_b - y_a;
+  const int cb = grp * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const float* o = orig + g * (long long)H * W;
   const float* p = pred + g * (long long)H * W;
-  const int nx = W - kWin + 1, ny = H - kWin + 1;
-  const int y_a = seg * rows_per_seg, y_b = min(ny, y_a + rows_per_seg);     // window rows [y_a, y_b)
   const int xc = cb * kColsPerWarp + 4 * lane;                               // this lane's first pixel column
-  const bool in_cols = xc + 3 < W;
+  const bool in_cols = cb < n_colblocks && xc + 3 < W;
   const double n_pix = (double)H * (double)W;
   const float mo = (float)(acc[g].so / n_pix), mp = (float)(acc[g].sp / n_pix);
   const float R = ord2f(acc[g].mx) - ord2f(acc[g].mn);        // data range (pass 1 has completed: stream order)
   const float c1 = (0.01f * R) * (0.01f * R), c2 = (0.03f * R) * (0.03f * R);
-  const float inv = 1.0f / 49.0f, cov_norm = 49.0f / 48.0f;
-  float V[4][4];               // x, y, xx + yy, xy (the two variances only ever appear as their sum)
+  const uint64_t MO2 = pk2(2.f * mo, 2.f * mo), MP2 = pk2(2.f * mp, 2.f * mp);
+  const uint64_t MO49 = pk2(49.f * mo, 49.f * mo), MP49 = pk2(49.f * mp, 49.f * mp);
+  const uint64_t C1 = pk2(2401.f * c1, 2401.f * c1), C2 = pk2(48.f * c2, 48.f * c2);
+  const uint64_t NEG2_49 = pk2(-2.f / 49.f, -2.f / 49.f), NEG1_49 = pk2(-1.f / 49.f, -1.f / 49.f);
+  // 0 / 1 weights of this lane's four windows (halo lanes, columns past the last complete window)
+  float wk[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) V[q][k] = 0.f;
-  // raw rows are fetched ahead of their use (a warp's rows are otherwise one dependent DRAM round trip each: with
-  // ~20 warps per SM that is ~20 KB in flight, a third of what the HBM needs): the entering row two iterations ahead,
-  // the leaving row (L1 / L2 resident) one ahead
+  for (int k = 0; k < 4; ++k) wk[k] = (cb < n_colblocks && lane < kColsPerWarp / 4 && xc + k < nx) ? 1.f : 0.f;
+  const uint64_t WK[2] = {pk2(wk[0], wk[1]), pk2(wk[2], wk[3])};
+  // vertical sums of u, v, u^2 + v^2, 2uv for the column pairs (0,1) and (2,3)
+  uint64_t Vx[2] = {0ull, 0ull}, Vy[2] = {0ull, 0ull}, Vq[2] = {0ull, 0ull}, Vc[2] = {0ull, 0ull};
+  // Raw rows are fetched ahead of their use (a warp's rows are otherwise one dependent DRAM round trip each): the
+  // entering row two iterations ahead into a rotating set of three register slots (the loop is unrolled by three, so
+  // the rotation is a renaming, not 16 moves), the leaving row (L1 / L2 resident) one ahead.  Lanes outside the image
+  // never load: their slots stay at (mean x, mean y), i.e. centred value 0.
   struct Raw { float4 a, b; };
   const int y_end = y_b + kWin - 1;                  // one past the last input row of the segment
-  auto fetch = [&](int y) -> Raw {
-    Raw r;
-    r.a = make_float4(mo, mo, mo, mo);               // outside the image: centred value 0
-    r.b = make_float4(mp, mp, mp, mp);
+  const Raw outside = {make_float4(mo, mo, mo, mo), make_float4(mp, mp, mp, mp)};
+  auto load = [&](Raw& r, int y) {
     if (in_cols && y < y_end) {
       r.a = __ldg(reinterpret_cast<const float4*>(o + (long long)y * W + xc));
       r.b = __ldg(reinterpret_cast<const float4*>(p + (long long)y * W + xc));
     }
-    return r;
-  };
-  auto centre = [&](const Raw& r, float (&u)[4], float (&v)[4]) {
-    u[0] = r.a.x - mo; u[1] = r.a.y - mo; u[2] = r.a.z - mo; u[3] = r.a.w - mo;
-    v[0] = r.b.x - mp; v[1] = r.b.y - mp; v[2] = r.b.z - mp; v[3] = r.b.w - mp;
   };
   double local = 0.0;
-  Raw n0 = fetch(y_a), n1 = fetch(y_a + 1), old = fetch(y_a);      // old: first needed at y = y_a + 7
-  for (int y = y_a; y < y_end; ++y) {
-    const Raw n2 = fetch(y + 2);
-    float u[4], v[4];
-    centre(n0, u, v);
+  Raw old = outside;
+  auto body = [&](const Raw& cur, int y) {
+    {
+      const uint64_t A[2] = {pk2(cur.a.x, cur.a.y), pk2(cur.a.z, cur.a.w)}, B[2] = {pk2(cur.b.x, cur.b.y), pk2(cur.b.z, cur.b.w)};
+      const uint64_t Ao[2] = {pk2(old.a.x, old.a.y), pk2(old.a.z, old.a.w)}, Bo[2] = {pk2(old.b.x, old.b.y), pk2(old.b.z, old.b.w)};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      V[0][k] += u[k]; V[1][k] += v[k];
-      V[2][k] = fmaf(u[k], u[k], V[2][k]); V[2][k] = fmaf(v[k], v[k], V[2][k]); V[3][k] = fmaf(u[k], v[k], V[3][k]);
-    }
-    n0 = n1;
-    n1 = n2;
-    if (y - y_a >= kWin) {
-      centre(old, u, v);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        V[0][k] -= u[k]; V[1][k] -= v[k];
-        V[2][k] = fmaf(-u[k], u[k], V[2][k]); V[2][k] = fmaf(-v[k], v[k], V[2][k]); V[3][k] = fmaf(-u[k], v[k], V[3][k]);
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t dx = sub2(A[h], Ao[h]), sx = sub2(add2(A[h], Ao[h]), MO2);
+        const uint64_t dy = sub2(B[h], Bo[h]), sy = sub2(add2(B[h], Bo[h]), MP2);
+        Vx[h] = add2(Vx[h], dx);
+        Vy[h] = add2(Vy[h], dy);
+        Vq[h] = fma2(dy, sy, fma2(dx, sx, Vq[h]));
+        Vc[h] = fma2(sx, dy, fma2(dx, sy, Vc[h]));
       }
     }
-    if (y - y_a >= kWin - 1) old = fetch(y + 1 - kWin);      // the row that leaves at the next iteration
-    if (y - y_a < kWin - 1) continue;              // (warp-uniform) the first complete window ends at row y_a + 6
-    float S[4][4];
+    if (y + 1 - y_a >= kWin) load(old, y + 1 - kWin);        // the row that leaves at the next iteration
+    if (y - y_a < kWin - 1) return;                          // (CTA-uniform) the first complete window ends at row y_a + 6
+    uint64_t S[4][2];                                        // window sums, windows (0,1) and (2,3)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float a0 = V[q][0], a1 = V[q][1], a2 = V[q][2], a3 = V[q][3];
-      const float b0 = __shfl_down_sync(0xffffffffu, a0, 1), b1 = __shfl_down_sync(0xffffffffu, a1, 1);
-      const float b2 = __shfl_down_sync(0xffffffffu, a2, 1), b3 = __shfl_down_sync(0xffffffffu, a3, 1);
-      const float d0 = __shfl_down_sync(0xffffffffu, a0, 2), d1 = __shfl_down_sync(0xffffffffu, a1, 2);
-      const float m = (a3 + b0) + (b1 + b2);       // common to the four windows
-      const float a12 = a1 + a2, bd = b3 + d0;
-      S[q][0] = (a0 + a12) + m;
-      S[q][1] = a12 + (m + b3);
-      S[q][2] = a2 + (m + bd);
-      S[q][3] = m + (bd + d1);
+      const uint64_t* V = q == 0 ? Vx : q == 1 ? Vy : q == 2 ? Vq : Vc;
+      float a0, a1, a2, a3;
+      upk2(V[0], a0, a1);
+      upk2(V[1], a2, a3);
+      // prefix / suffix sums of the lane's own four columns; the neighbours contribute theirs: 4 shuffles, 11 additions
+      const float l2 = a0 + a1, r2 = a2 + a3, l3 = l2 + a2, r3 = a1 + r2, t = l2 + r2;
+      const float l3n = __shfl_down_sync(0xffffffffu, l3, 1), tn = __shfl_down_sync(0xffffffffu, t, 1);
+      const float l1nn = __shfl_down_sync(0xffffffffu, a0, 2), l2nn = __shfl_down_sync(0xffffffffu, l2, 2);
+      S[q][0] = pk2(t + l3n, r3 + tn);                       // columns 0..6, 1..7
+      S[q][1] = pk2(r2 + (tn + l1nn), a3 + (tn + l2nn));     // columns 2..8, 3..9
     }
-    float row = 0.f;
+    uint64_t ROW = 0ull;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float s0 = S[0][k] * inv, s1 = S[1][k] * inv;
-      const float vsum = cov_norm * fmaf(-s1, s1, fmaf(-s0, s0, S[2][k] * inv));        // var x + var y
-      const float vxy = cov_norm * fmaf(-s0, s1, S[3][k] * inv);
-      const float ux = s0 + mo, uy = s1 + mp;
-      const float num = fmaf(2.f * ux, uy, c1) * fmaf(2.f, vxy, c2);
-      const float den = fmaf(uy, uy, fmaf(ux, ux, c1)) * (vsum + c2);
-      if (lane < kColsPerWarp / 4 && xc + k < nx) row += __fdividef(num, den);
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t Sx = S[0][h], Sy = S[1][h];
+      const uint64_t Ux = add2(Sx, MO49), Uy = add2(Sy, MP49);
+      const uint64_t n1_ = fma2(add2(Ux, Ux), Uy, C1);
+      const uint64_t d1_ = fma2(Uy, Uy, fma2(Ux, Ux, C1));
+      const uint64_t n2_ = fma2(mul2(Sx, Sy), NEG2_49, add2(S[3][h], C2));
+      const uint64_t d2_ = fma2(fma2(Sx, Sx, mul2(Sy, Sy)), NEG1_49, add2(S[2][h], C2));
+      float den0, den1, r0, r1;
+      upk2(mul2(d1_, d2_), den0, den1);
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(den0));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(den1));
+      ROW = fma2(mul2(mul2(n1_, n2_), pk2(r0, r1)), WK[h], ROW);
     }
-    local += (double)row;
+    float row0, row1;
+    upk2(ROW, row0, row1);
+    local += (double)(row0 + row1);
+  };
+  Raw r0 = outside, r1 = outside, r2 = outside;
+  load(r0, y_a);
+  load(r1, y_a + 1);
+  for (int y = y_a; y < y_end; y += 3) {
+    load(r2, y + 2);
+    body(r0, y);
+    if (y + 1 >= y_end) break;
+    load(r0, y + 3);
+    body(r1, y + 1);
+    if (y + 2 >= y_end) break;
+    load(r1, y + 4);
+    body(r2, y + 2);
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
   if (lane == 0) atomicAdd(&acc[g].ssim_sum, local);
+  }  // next (pair, row range) of this CTA
 }
 
 __global__ void finalize_kernel(const Acc* __restrict__ acc, long long N, int H, int W, double* __restrict__ out) {
@@ -329,28 +400,33 @@ extern "C" int mrinr_image_metrics(const float* d_original, const float* d_predi
   metrics::Acc* acc = static_cast<metrics::Acc*>(d_scratch);
   const long long n = (long long)H * W;
   metrics::init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(acc, N);
-  long long bx = (n + 256 * 8 - 1) / (256 * 8);
-  if (bx < 1) bx = 1;
+  // reduction pass: ~100 pixels of each image per thread when there are many pairs (the block reduction and the six
+  // atomics are per CTA), more CTAs per pair when there are few
+  long long bx = (2368 + N - 1) / N;
+  if (bx < 4) bx = 4;
   if (bx > 64) bx = 64;
+  while (bx > 1 && bx * 256 * 8 > n) bx >>= 1;
   metrics::reduce_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, st>>>(d_original, d_predicted, n, acc);
   const int nx = W - metrics::kWin + 1, ny = H - metrics::kWin + 1;
   if (W % 4 == 0 && aligned16(d_original) && aligned16(d_predicted)) {
-    // row-streaming kernel: enough row segments for ~32 warps per SM, at least 16 window rows each
+    // row-streaming kernel: one wave of persistent CTAs (<= 4 column blocks = warps each), every CTA an equal share of
+    // all window rows, at least 16 rows
     const int n_cb = (nx + metrics::kColsPerWarp - 1) / metrics::kColsPerWarp;
-    int sms = 148;
+    const int wpb = n_cb < metrics::kStreamMaxWarps ? n_cb : metrics::kStreamMaxWarps;
+    const int cb_groups = (n_cb + wpb - 1) / wpb;
+    int sms = 148, per_sm = 4;
     {
       int dev = 0;
       MRINR_CUDA(cudaGetDevice(&dev));
       MRINR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      MRINR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, metrics::ssim_stream_kernel, 32 * wpb, 0));
+      if (per_sm < 1) per_sm = 1;
     }
-    long long n_seg = (32ll * sms + N * n_cb - 1) / (N * n_cb);
-    if (n_seg > (ny + 15) / 16) n_seg = (ny + 15) / 16;
-    if (n_seg < 1) n_seg = 1;
-    const int rows_per_seg = (int)((ny + n_seg - 1) / n_seg);
-    n_seg = (ny + rows_per_seg - 1) / rows_per_seg;
-    const int units = (int)(n_cb * n_seg);
-    metrics::ssim_stream_kernel<<<dim3((unsigned)((units + 3) / 4), (unsigned)N), 128, 0, st>>>(
-        d_original, d_predicted, H, W, n_cb, (int)n_seg, rows_per_seg, acc);
+    const long long rows_all = (long long)cb_groups * N * ny;
+    long long grid = (long long)sms * per_sm;
+    if (grid > (rows_all + 15) / 16) grid = (rows_all + 15) / 16;
+    if (grid < 1) grid = 1;
+    metrics::ssim_stream_kernel<<<(unsigned)grid, 32 * wpb, 0, st>>>(d_original, d_predicted, H, W, n_cb, cb_groups, N, acc);
   } else {
     dim3 grid((nx + metrics::kT - 1) / metrics::kT, (ny + metrics::kT - 1) / metrics::kT, (unsigned)N);
     metrics::ssim_kernel<<<grid, 256, 0, st>>>(d_original, d_predicted, H, W, acc);

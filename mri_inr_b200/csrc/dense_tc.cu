@@ -19,7 +19,7 @@
 // Per CTA: one 128-row tile, all N columns (N = 64, 128 or 256), K in slabs of 32 through a 2-stage ring (96 KB for
 // N = 256), so that TWO CTAs are resident per SM: one CTA's prologue / epilogue (all latency) hides behind the
 // other's MMAs.  (With one 192 KB CTA per SM the tensor pipe was 18 % active, profiles/r01_ncu_dense_split.txt.)
-//   warps 0-3  A producers: thread = row; load 64 fp32 (one slab ahead, in registers), split, write both halves in
+//   warps 0-3  A producers: coalesced loads of the fp32 rows (two slabs ahead, in registers), split, write both halves in
 //              the UMMA K-major core-matrix layout; afterwards the epilogue (tcgen05.ld, bias, activation, store)
 //   warp 4     MMA issuer (converged warp + elect.sync); owns the TMEM allocation
 //   warp 5     weight producer: one cp.async.bulk per slab (hi and lo halves are contiguous in the packed array)
@@ -167,10 +167,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     static_assert(kSlabK == 32 && 2 * kKc == 8, "a warp instruction covers 4 rows of one 32-column slab");
-    float4 r[2 * kKc];
-    if (n_slabs > 0) load_slab(0, r);
+    // The operand rows are prefetched TWO slabs ahead in registers (three rotating sets; the loop is unrolled by three
+    // so the rotation is a renaming): with one slab ahead a CTA had 16 KB in flight and every slab was a dependent
+    // DRAM round trip -- the kernel ran at ~3 TB/s of operand traffic with the tensor pipe a third busy.
     const int st_off = (lq >> 1) * (kBM * 16) + (warp * 32 + lrow) * 16 + (lq & 1) * 8;    // + 64 i
-    for (int slab = 0; slab < n_slabs; ++slab) {
+    auto step = [&](int slab, const float4 (&r)[2 * kKc]) {
       const int st = slab % kStages;
       mbar_wait(bar_empty(st), ((slab / kStages) & 1u) ^ 1u, P.errflag, 21);
       uint8_t* a_hi = smem + st * C::kStageBytes + st_off;
@@ -182,10 +183,22 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
         *reinterpret_cast<uint2*>(a_hi + i * 64) = hi;
         *reinterpret_cast<uint2*>(a_lo + i * 64) = lo;
       }
-      if (slab + 1 < n_slabs) load_slab(slab + 1, r);      // in flight while the tensor core works on this slab
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_afull(st));
+    };
+    float4 r0[2 * kKc], r1[2 * kKc], r2[2 * kKc];
+    if (n_slabs > 0) load_slab(0, r0);
+    if (n_slabs > 1) load_slab(1, r1);
+    for (int slab = 0; slab < n_slabs; slab += 3) {
+      if (slab + 2 < n_slabs) load_slab(slab + 2, r2);
+      step(slab, r0);
+      if (slab + 1 >= n_slabs) break;
+      if (slab + 3 < n_slabs) load_slab(slab + 3, r0);
+      step(slab + 1, r1);
+      if (slab + 2 >= n_slabs) break;
+      if (slab + 4 < n_slabs) load_slab(slab + 4, r1);
+      step(slab + 2, r2);
     }
     // ---- epilogue: this thread owns row `row` (TMEM lane 32*warp + lane) ----
     mbar_wait(bar_acc, 0u, P.errflag, 22);

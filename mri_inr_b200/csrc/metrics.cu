@@ -213,6 +213,7 @@ ssim_kernel(const float* __restrict__ orig, const float* __restrict__ pred, int 
 // also packed over window pairs.  ~55 instructions per window (first streaming version: 100; tiled kernel: 170).
 constexpr int kColsPerWarp = 120;
 constexpr int kStreamMaxWarps = 4;
+constexpr int kRowsPerSeg = 32;
 
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
   uint64_t r;
@@ -248,19 +249,20 @@ ssim_stream_kernel(const float* __restrict__ orig, const float* __restrict__ pre
                    int cb_groups, long long N, Acc* __restrict__ acc) {
   const int lane = threadIdx.x & 31;
   const int nx = W - kWin + 1, ny = H - kWin + 1;
-  // Work = cb_groups x N x ny window rows, cut into gridDim.x equal contiguous ranges (CTA-uniform bounds): every CTA
-  // gets the same number of rows whatever N is (with one (pair, segment) per CTA, 2 112 CTAs on 1 036 slots ran as two
-  // full waves and a nearly empty third).  A range restarts the running sums where it begins and at every image boundary.
-  const long long rows_all = (long long)cb_groups * N * ny;
-  long long r = rows_all * blockIdx.x / gridDim.x;
-  const long long r_end = rows_all * (blockIdx.x + 1) / gridDim.x;
-  while (r < r_end) {
-  const int grp = (int)(r / (N * ny));
-  const long long rg = r - (long long)grp * N * ny;
-  const long long g = rg / ny;
-  const int y_a = (int)(rg - g * ny);
-  const int y_b = (int)min((long long)ny, y_a + (r_end - r));               // window rows [y_a, y_b) of pair g
-  r += y_b - y_a;
+  // Work units = (column-block group, image pair, segment of kRowsPerSeg window rows); gridDim.x persistent CTAs walk
+  // equal contiguous ranges of them (CTA-uniform bounds).  The segmentation of an image is FIXED -- it depends neither
+  // on the batch size nor on the grid -- so an image's result does not depend on the batch it is evaluated in; ten
+  // segments per 320-row image keep the ranges balanced to 1 % (one (pair, half image) per CTA ran as two full waves
+  // and a nearly empty third) at the price of six warm-up rows (vertical update only, a quarter of a full row) per segment.
+  const int n_seg = (ny + kRowsPerSeg - 1) / kRowsPerSeg;
+  const long long units = (long long)cb_groups * N * n_seg;
+  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+  for (long long u = units * blockIdx.x / gridDim.x; u < u_end; ++u) {
+  const int grp = (int)(u / (N * n_seg));
+  const long long ug = u - (long long)grp * N * n_seg;
+  const long long g = ug / n_seg;
+  const int y_a = (int)(ug - g * n_seg) * kRowsPerSeg;
+  const int y_b = min(ny, y_a + kRowsPerSeg);                               // window rows [y_a, y_b) of pair g
   const int cb = grp * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const float* o = orig + g * (long long)H * W;
   const float* p = pred + g * (long long)H * W;
@@ -361,7 +363,7 @@ ssim_stream_kernel(const float* __restrict__ orig, const float* __restrict__ pre
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
   if (lane == 0) atomicAdd(&acc[g].ssim_sum, local);
-  }  // next (pair, row range) of this CTA
+  }  // next unit of this CTA
 }
 
 __global__ void finalize_kernel(const Acc* __restrict__ acc, long long N, int H, int W, double* __restrict__ out) {
@@ -400,17 +402,17 @@ extern "C" int mrinr_image_metrics(const float* d_original, const float* d_predi
   metrics::Acc* acc = static_cast<metrics::Acc*>(d_scratch);
   const long long n = (long long)H * W;
   metrics::init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(acc, N);
-  // reduction pass: ~100 pixels of each image per thread when there are many pairs (the block reduction and the six
-  // atomics are per CTA), more CTAs per pair when there are few
-  long long bx = (2368 + N - 1) / N;
-  if (bx < 4) bx = 4;
+  // reduction pass: ~100 pixels of each image per thread (the block reduction and the six atomics are per CTA).  The
+  // split of an image over CTAs depends on the image size only, never on N: an image's partial sums are formed the
+  // same way in every batch.
+  long long bx = (n >> 2) / (256 * 24);
+  if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
-  while (bx > 1 && bx * 256 * 8 > n) bx >>= 1;
   metrics::reduce_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, st>>>(d_original, d_predicted, n, acc);
   const int nx = W - metrics::kWin + 1, ny = H - metrics::kWin + 1;
   if (W % 4 == 0 && aligned16(d_original) && aligned16(d_predicted)) {
     // row-streaming kernel: one wave of persistent CTAs (<= 4 column blocks = warps each), every CTA an equal share of
-    // all window rows, at least 16 rows
+    // the (pair, 32-row segment) units
     const int n_cb = (nx + metrics::kColsPerWarp - 1) / metrics::kColsPerWarp;
     const int wpb = n_cb < metrics::kStreamMaxWarps ? n_cb : metrics::kStreamMaxWarps;
     const int cb_groups = (n_cb + wpb - 1) / wpb;
@@ -422,10 +424,9 @@ extern "C" int mrinr_image_metrics(const float* d_original, const float* d_predi
       MRINR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, metrics::ssim_stream_kernel, 32 * wpb, 0));
       if (per_sm < 1) per_sm = 1;
     }
-    const long long rows_all = (long long)cb_groups * N * ny;
+    const long long units = (long long)cb_groups * N * ((ny + metrics::kRowsPerSeg - 1) / metrics::kRowsPerSeg);
     long long grid = (long long)sms * per_sm;
-    if (grid > (rows_all + 15) / 16) grid = (rows_all + 15) / 16;
-    if (grid < 1) grid = 1;
+    if (grid > units) grid = units;
     metrics::ssim_stream_kernel<<<(unsigned)grid, 32 * wpb, 0, st>>>(d_original, d_predicted, H, W, n_cb, cb_groups, N, acc);
   } else {
     dim3 grid((nx + metrics::kT - 1) / metrics::kT, (ny + metrics::kT - 1) / metrics::kT, (unsigned)N);

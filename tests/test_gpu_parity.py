@@ -421,6 +421,12 @@ def test_image_metrics_match_oracle(hw):
     assert abs(metrics.calculate_ssim(a, b) - got[1, 1]) < 1e-12
     assert abs(metrics.calculate_nrmse(a, b) - got[1, 2]) < 1e-12
     assert abs(metrics.calculate_data_range(a, b) - ometrics.data_range(full[1], pred[1])) < 1e-6
+    # ... and an image's metrics do not depend on the batch it is evaluated in (the kernels' segmentation of an image
+    # is fixed; only the order of a handful of fp64 atomics varies)
+    big_f = torch.from_numpy(full).to(DEV).repeat(37, 1, 1)
+    big_p = torch.from_numpy(pred).to(DEV).repeat(37, 1, 1)
+    big = ops.image_metrics(big_f, big_p).cpu().numpy()
+    assert np.abs(big.reshape(37, 4, 3) - got[None]).max() < 1e-9
 
 
 @pytest.mark.parametrize("hw", [(320, 320), (64, 80), (30, 50), (96, 75), (1024, 8), (2, 2)])

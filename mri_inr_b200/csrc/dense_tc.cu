@@ -42,7 +42,12 @@ constexpr int kThreads = 192;
 #define MRINR_DENSE_CLUSTER 2
 #endif
 constexpr int kCluster = MRINR_DENSE_CLUSTER;
-constexpr int kAHalfBytes = kBM * kSlabK * 2;          // 8 KB: [4 kc][128 rows][8] fp16
+// A operand half (hi or lo) of a stage: [4 kc][128 rows][8] fp16, K chunks kALbo bytes apart.  The 64 bytes of padding
+// per chunk spread a producer warp's store instruction (4 rows x 4 K chunks x 16 bytes) over all 32 banks: with chunks
+// exactly 2 KB apart the four K chunks of a row fell on the same banks (4-way conflict, ncu: 75 % of the kernel's
+// shared-memory wavefronts were conflict replays on a shared-memory port that also feeds the tensor core).
+constexpr int kALbo = kBM * 16 + 64;
+constexpr int kAHalfBytes = kKc * kALbo;
 
 template <int N>
 struct Cfg {
@@ -150,8 +155,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
 
   if (warp < 4) {
     // =========================== A producers, then epilogue ===========================
-    const long long row = (long long)blockIdx.x * kBM + tid;
-    const bool live = row < P.M;
     // Loads are COALESCED: one warp instruction covers 4 rows x 128 bytes (lane -> row 4i + lane/8, floats 4 (lane%8)
     // .. +3 of the slab) instead of 32 different lines (thread = row), which kept the L1 tag stage busy 8x longer for
     // the same bytes.  A lane then owns half of a 16-byte UMMA entry (4 of its 8 K values) and stores 8 bytes.
@@ -170,7 +173,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
     // The operand rows are prefetched TWO slabs ahead in registers (three rotating sets; the loop is unrolled by three
     // so the rotation is a renaming): with one slab ahead a CTA had 16 KB in flight and every slab was a dependent
     // DRAM round trip -- the kernel ran at ~3 TB/s of operand traffic with the tensor pipe a third busy.
-    const int st_off = (lq >> 1) * (kBM * 16) + (warp * 32 + lrow) * 16 + (lq & 1) * 8;    // + 64 i
+    const int st_off = (lq >> 1) * kALbo + (warp * 32 + lrow) * 16 + (lq & 1) * 8;    // + 64 i
     auto step = [&](int slab, const float4 (&r)[2 * kKc]) {
       const int st = slab % kStages;
       mbar_wait(bar_empty(st), ((slab / kStages) & 1u) ^ 1u, P.errflag, 21);
@@ -200,30 +203,43 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
       if (slab + 4 < n_slabs) load_slab(slab + 4, r1);
       step(slab + 2, r2);
     }
-    // ---- epilogue: this thread owns row `row` (TMEM lane 32*warp + lane) ----
+    // ---- epilogue: this thread owns row `row` (TMEM lane 32*warp + lane), 32 columns per trip ----
+    // A thread holds 128 contiguous bytes of ITS row; storing them directly makes every store instruction of a warp
+    // touch 32 rows x 16 bytes (half sectors, 1 KB apart) -- ncu: the epilogue was 45 % of a CTA's life, stalled at the
+    // loop top on the previous trip's store addresses (the store queue).  The warp therefore transposes each 32 x 128 B
+    // block through shared memory (the stage ring is free once the last MMA has completed; chunk index XOR row so that
+    // both directions are conflict-free) and writes whole 128-byte lines: 4 rows per instruction.
     mbar_wait(bar_acc, 0u, P.errflag, 22);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float* crow = P.c + row * P.ldc;
+    uint8_t* stg = smem + warp * 4096;
+    const int orow = lane >> 3, och = lane & 7;
+    const long long row_base = (long long)blockIdx.x * kBM + warp * 32;
 #pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)c0, v);
       tmem_ld_wait();
-      float y[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = __uint_as_float(v[i]);
-        x += s_bias[c0 + i];
-        if (P.act == 1) x = fmaxf(x, 0.f);
-        else if (P.act == 2) x = x > 0.f ? x : x * P.slope;
-        y[i] = x;
-      }
-      if (live) {
+      for (int j = 0; j < 8; ++j) {
+        const float4 bj = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
+        float y[4] = {__uint_as_float(v[4 * j]) + bj.x, __uint_as_float(v[4 * j + 1]) + bj.y,
+                      __uint_as_float(v[4 * j + 2]) + bj.z, __uint_as_float(v[4 * j + 3]) + bj.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<float4*>(crow + c0 + 4 * i) = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) {
+          if (P.act == 1) y[i] = fmaxf(y[i], 0.f);
+          else if (P.act == 2) y[i] = y[i] > 0.f ? y[i] : y[i] * P.slope;
+        }
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
       }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = orow + 4 * k;
+        const float4 t = *reinterpret_cast<const float4*>(stg + r * 128 + ((och ^ (r & 7)) << 4));
+        if (row_base + r < P.M) *reinterpret_cast<float4*>(P.c + (row_base + r) * P.ldc + c0 + 4 * och) = t;
+      }
+      __syncwarp();
     }
     tc_fence_before();
   } else if (warp == 4) {
@@ -237,13 +253,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = smem_u32(smem + st * C::kStageBytes);
-        const uint64_t a_hi = make_smem_desc(sa, kBM * 16, 128);
-        const uint64_t a_lo = make_smem_desc(sa + kAHalfBytes, kBM * 16, 128);
+        const uint64_t a_hi = make_smem_desc(sa, kALbo, 128);
+        const uint64_t a_lo = make_smem_desc(sa + kAHalfBytes, kALbo, 128);
         const uint64_t b_hi = make_smem_desc(sa + 2 * kAHalfBytes, N * 16, 128);
         const uint64_t b_lo = make_smem_desc(sa + 2 * kAHalfBytes + C::kWHalfBytes, N * 16, 128);
 #pragma unroll
         for (int k = 0; k < kSlabK / 16; ++k) {
-          const uint64_t da = (uint64_t)((k * 2 * kBM * 16) >> 4);
+          const uint64_t da = (uint64_t)((k * 2 * kALbo) >> 4);
           const uint64_t db = (uint64_t)((k * 2 * N * 16) >> 4);
           // small terms first
           umma_f16(tmem_base, a_lo + da, b_hi + db, idesc, (slab | k) != 0 ? 1u : 0u);

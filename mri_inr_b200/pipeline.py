@@ -20,6 +20,27 @@ from .modulated_siren import ModulatedSiren
 from .tiling import _weights_on
 
 
+def host_schedule(n: int, chunk: int):
+    """``[(start, count), ...]`` for ``reconstruct_from_host``: with more than two chunks of work the first and the last
+    chunk are ``chunk // 4`` slices -- the upload of the first and the download of the last chunk are the only transfers
+    that nothing hides (3.2 ms of a 145 ms step at 8 GPUs with uniform 216-slice chunks) -- and the slices in between
+    are split evenly into chunks of at most ``chunk``."""
+    if n <= 0:
+        return []
+    edge = chunk // 4
+    if edge < 1 or n <= 2 * chunk:
+        return [(s0, min(chunk, n - s0)) for s0 in range(0, n, chunk)]
+    middle = n - 2 * edge
+    k = -(-middle // chunk)
+    base, extra = divmod(middle, k)
+    sizes = [edge] + [base + (1 if i < extra else 0) for i in range(k)] + [edge]
+    out, s0 = [], 0
+    for c in sizes:
+        out.append((s0, c))
+        s0 += c
+    return out
+
+
 class ReconstructionPipeline:
     def __init__(self, model: ModulatedSiren, chunk_slices: int = 256):
         self.model = model
@@ -139,7 +160,8 @@ class ReconstructionPipeline:
 
         Chunks are double-buffered over three streams -- upload of chunk i+1, compute of chunk i and download of
         chunk i-1 run concurrently (PCIe is full duplex and the copy engines are independent of the SMs) -- so the
-        transfers cost one chunk of latency instead of two full passes.  On return all work has been enqueued and
+        transfers cost one chunk of latency instead of two full passes; the first and the last chunk are a quarter of
+        the others (``host_schedule``), because only THEIR upload / download is exposed.  On return all work has been enqueued and
         the CURRENT stream waits for it: synchronise that stream (or the device) before reading ``host_out``."""
         m = self.model
         m._check_inference()
@@ -166,8 +188,7 @@ class ReconstructionPipeline:
         start.record(comp)
         s_in.wait_event(start)          # nothing of this call may overtake earlier work on the caller's stream
         s_out.wait_event(start)
-        for i, s0 in enumerate(range(0, N, cs)):
-            n = min(cs, N - s0)
+        for i, (s0, n) in enumerate(host_schedule(N, cs)):
             k = i & 1
             with torch.cuda.stream(s_in):
                 if i >= 2:

@@ -227,3 +227,21 @@ def test_bench_chunking_and_reference_arm_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["num_layers"] == 3
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+
+
+def test_host_schedule_covers_every_slice_once_with_short_edge_chunks():
+    """pipeline.host_schedule: contiguous cover of [0, n), no chunk above the buffer size, and -- with more than two
+    chunks of work -- a first and a last chunk of chunk // 4 slices (the only exposed transfers of the e2e leg)."""
+    from mri_inr_b200.pipeline import host_schedule
+
+    for n, c in [(10340, 235), (1293, 216), (1, 235), (470, 235), (471, 235), (0, 235), (7, 2), (100, 3), (5170, 235)]:
+        sch = host_schedule(n, c)
+        assert sum(k for _, k in sch) == n
+        assert all(0 < k <= c for _, k in sch)
+        assert all(sch[i][0] + sch[i][1] == sch[i + 1][0] for i in range(len(sch) - 1))
+        if sch:
+            assert sch[0][0] == 0
+        if n > 2 * c and c >= 4:
+            assert sch[0][1] == c // 4 and sch[-1][1] == c // 4
+            mid = [k for _, k in sch[1:-1]]
+            assert max(mid) - min(mid) <= 1

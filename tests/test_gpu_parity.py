@@ -880,3 +880,27 @@ def test_new_parameter_values_refresh_the_packed_handle_in_place(precision, tol)
     with torch.no_grad():
         m(tiles)
     assert m._pack is not pack                                      # another precision: a new handle
+
+
+def test_graphed_reconstruction_is_bit_identical_and_follows_new_weights():
+    """ReconstructionPipeline.reconstruct_graphed: a chunk captured into a CUDA graph (nothing in it synchronises or
+    allocates: the boundary contract of SURVEY section 8b) replays bit-identically to the eager launches, for new
+    inputs and -- without re-capturing -- for new parameter values (the packed handle is refreshed in place)."""
+    from mri_inr_b200.pipeline import ReconstructionPipeline
+
+    name, sd_kw, act, model_kw = MODEL_CASES[1]
+    m, sd = _model(sd_kw, act, model_kw, "fp16")
+    pipe = ReconstructionPipeline(m, chunk_slices=2)
+    imgs = [torch.from_numpy(np.stack([synth_image(500 + 3 * k + i, 96, 80) for i in range(3)])).to(DEV) for k in range(3)]
+    imgs[1][1, :40] = 0.0                                 # black patches: the compaction path is captured too
+    for x in imgs:
+        want = pipe.reconstruct(x).clone()
+        got = pipe.reconstruct_graphed(x)
+        assert torch.equal(got, want)
+    n_graphs = len(pipe._buf["graphs"])
+    with torch.no_grad():
+        for prm in m.parameters():
+            prm.mul_(1.01)
+    want = pipe.reconstruct(imgs[0]).clone()
+    got = pipe.reconstruct_graphed(imgs[0])
+    assert torch.equal(got, want) and len(pipe._buf["graphs"]) == n_graphs

@@ -4,8 +4,9 @@
 // DFT per thread (k1 fixed).  The 16-point DFT is 4 x 4 (nine constant twiddles), the 20-point DFT is the prime-factor
 // form 4 x 5 (4 and 5 are coprime: n = 5 a + 4 b, k = 5 c + 16 d mod 20, no twiddles at all).  Every index map is a
 // compile-time permutation of registers.  w = exp(sgn 2 pi i / n), sgn = +1 for the inverse transform (INV).
-// Plain C++ apart from the MRINR_HD qualifier: tests/test_fft320_host.py compiles it with g++ and checks the three
-// routines against naive fp64 DFTs.
+// Plain C++ apart from the MRINR_HD qualifier and the packed device versions of add / sub / axpy / scale:
+// tests/test_fft320_host.py compiles it with g++ and checks the three routines against naive fp64 DFTs (the GPU
+// tests check the device versions against numpy fp64).
 #pragma once
 #ifdef __CUDACC__
 #define MRINR_HD __device__ __forceinline__
@@ -20,8 +21,48 @@ struct C {
   float x, y;
 };
 MRINR_HD C mk(float x, float y) { C c; c.x = x; c.y = y; return c; }
+#ifdef __CUDA_ARCH__
+// On the device a complex value is one packed fp32 pair: complex add / subtract / real scaling are ONE instruction
+// (add.f32x2 / sub.f32x2 / fma.rn.f32x2) instead of two -- the columns pass of the 320-point transform is issue-bound.
+// Each packed operation rounds its two halves exactly like the two scalar operations it replaces.
+__device__ __forceinline__ unsigned long long pk(C a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ C upk(unsigned long long v) {
+  C c;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(v));
+  return c;
+}
+__device__ __forceinline__ C add(C a, C b) {
+  unsigned long long r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+  return upk(r);
+}
+__device__ __forceinline__ C sub(C a, C b) {
+  unsigned long long r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+  return upk(r);
+}
+// acc + c * t (c real)
+__device__ __forceinline__ C axpy(C acc, float c, C t) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(t)), "l"(pk(mk(c, c))), "l"(pk(acc)));
+  return upk(r);
+}
+// c * t (c real)
+__device__ __forceinline__ C scale(float c, C t) {
+  unsigned long long r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(t)), "l"(pk(mk(c, c))));
+  return upk(r);
+}
+#else
 MRINR_HD C add(C a, C b) { return mk(a.x + b.x, a.y + b.y); }
 MRINR_HD C sub(C a, C b) { return mk(a.x - b.x, a.y - b.y); }
+MRINR_HD C axpy(C acc, float c, C t) { return mk(acc.x + c * t.x, acc.y + c * t.y); }
+MRINR_HD C scale(float c, C t) { return mk(c * t.x, c * t.y); }
+#endif
 // a * (c + i s)
 MRINR_HD C mulc(C a, float c, float s) { return mk(a.x * c - a.y * s, a.x * s + a.y * c); }
 // a * (sgn i)
@@ -44,10 +85,10 @@ MRINR_HD void dft5(C& v0, C& v1, C& v2, C& v3, C& v4) {
   constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;     // cos(2 pi / 5), cos(4 pi / 5)
   constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;      // sin(2 pi / 5), sin(4 pi / 5)
   const C t1 = add(v1, v4), t2 = add(v2, v3), t3 = sub(v1, v4), t4 = sub(v2, v3);
-  const C m1 = mk(v0.x + c1 * t1.x + c2 * t2.x, v0.y + c1 * t1.y + c2 * t2.y);
-  const C m2 = mk(v0.x + c2 * t1.x + c1 * t2.x, v0.y + c2 * t1.y + c1 * t2.y);
-  const C n1 = muli<INV>(mk(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
-  const C n2 = muli<INV>(mk(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+  const C m1 = axpy(axpy(v0, c1, t1), c2, t2);
+  const C m2 = axpy(axpy(v0, c2, t1), c1, t2);
+  const C n1 = muli<INV>(axpy(scale(s1, t3), s2, t4));
+  const C n2 = muli<INV>(axpy(scale(s2, t3), -s1, t4));
   v0 = add(v0, add(t1, t2));
   v1 = add(m1, n1);
   v4 = sub(m1, n1);

@@ -116,6 +116,10 @@ int run_pack_split(const float* w, int N, int K, uint16_t* out, cudaStream_t st)
 int launch_dense_split(const float* a1, long long lda1, int K1, const float* a2, long long lda2, int K2,
                        const uint16_t* w_packed, const float* bias, int N, int act, float slope, float* c,
                        long long ldc, long long M, int32_t* errflag, cudaStream_t st);
+int launch_dense_chain256(int n, const float* const* a1, const long long* lda1, const int* K1, const float* const* a2,
+                          const long long* lda2, const int* K2, const uint16_t* const* w_packed,
+                          const float* const* bias, float* const* c, const long long* ldc, int act, float slope,
+                          long long M, int32_t* errflag, cudaStream_t st);
 int launch_encoder_conv(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,
                         const float* b2, float* d_out, int num_sms, cudaStream_t st);
 int launch_encoder_conv_tc(const float* d_patches, long long B, const float* w1, const float* b1, const float* w2,

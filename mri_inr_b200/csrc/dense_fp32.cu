@@ -394,9 +394,29 @@ extern "C" int mrinr_modulator_forward(const MrinrPacked* p, const float* d_late
   MRINR_REQUIRE(B >= 0, MRINR_E_ARG, "mrinr_modulator_forward: negative batch");
   if (B == 0) return 0;
   if (p->mod_tc) {
-    // tensor cores: one split-fp16 product per layer; layer l reads h_{l-1} = d_mods[l-1] and the latent
+    // tensor cores: split-fp16 products; layer l reads h_{l-1} = d_mods[l-1] and the latent
     MRINR_REQUIRE(aligned16(d_latent) && aligned16(d_mods), MRINR_E_ALIGN, "mrinr_modulator_forward: buffers must be 16-byte aligned");
     const size_t plane = (size_t)B * p->H;
+    if (p->H == 256 && p->L <= 16) {
+      // every layer in ONE launch: a CTA walks all layers of its 128 patches (dense_tc.cu: dense_chain_kernel)
+      const float* a1[16]; const float* a2[16]; const uint16_t* w[16]; const float* bias[16]; float* c[16];
+      long long lda1[16], lda2[16], ldc[16];
+      int K1[16], K2[16];
+      for (int l = 0; l < p->L; ++l) {
+        a1[l] = l == 0 ? d_latent : d_mods + (size_t)(l - 1) * plane;
+        lda1[l] = l == 0 ? p->Z : p->H;
+        K1[l] = l == 0 ? p->Z : p->H;
+        a2[l] = l == 0 ? nullptr : d_latent;
+        lda2[l] = l == 0 ? 0 : p->Z;
+        K2[l] = l == 0 ? 0 : p->Z;
+        w[l] = p->d_mod_ws + p->mod_ws_off[l];
+        bias[l] = p->d_mod_bias + (size_t)l * p->H;
+        c[l] = d_mods + (size_t)l * plane;
+        ldc[l] = p->H;
+      }
+      return launch_dense_chain256(p->L, a1, lda1, K1, a2, lda2, K2, w, bias, c, ldc, /*relu*/ 1, 0.f, B, p->d_errflag,
+                                   (cudaStream_t)stream);
+    }
     int rc = launch_dense_split(d_latent, p->Z, p->Z, nullptr, 0, 0, p->d_mod_ws + p->mod_ws_off[0], p->d_mod_bias, p->H,
                                 /*relu*/ 1, 0.f, d_mods, p->H, B, p->d_errflag, (cudaStream_t)stream);
     for (int l = 1; l < p->L && rc == 0; ++l)

@@ -294,6 +294,224 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2) 
   if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
+// ---- a CHAIN of dense layers in one launch (the modulator: modulated_siren.py:325-343) ---------------------------------
+// Layer l+1 of the modulator reads rows of layer l's output and of the latent -- only the SAME 128 rows the CTA has
+// just produced -- so a CTA can walk all layers of its row tile without any grid-wide synchronisation: "all layers'
+// modulations for a batch of latents in one launch" (north_star (2)).  The pipeline state runs on across layers (slab
+// counter, stage parities); the producer warps are the epilogue warps, so a layer's accumulator has been read before the
+// first operand slab of the next layer is produced, and the weight producer streams the next layer's slabs underneath
+// the epilogue.  A layer's output goes to global memory (it is an output: mods[l]) and comes back as the next layer's
+// operand through L2 (ld.global.cg after a block-level fence: each warp re-reads exactly the rows it stored).
+// Because the stage ring stays live, the epilogue has its own 2 KB per warp of transpose space (16 columns per trip:
+// 64-byte row segments, two full sectors).
+constexpr int kMaxChain = 16;
+struct ChainLayer {
+  const float* a1; long long lda1; int K1;
+  const float* a2; long long lda2; int K2;
+  const uint16_t* w;      // packed by pack_split_kernel
+  const float* bias;      // [N] or null
+  float* c; long long ldc;
+};
+struct ChainParams {
+  ChainLayer layer[kMaxChain];
+  int n_layers;
+  long long M;
+  int act;                // 0 none, 1 relu, 2 leaky relu
+  float slope;
+  int32_t* errflag;
+};
+
+template <int N>
+struct ChainCfg {
+  static constexpr int kOffStg = kStages * Cfg<N>::kStageBytes;      // 4 warps x [32 rows][64 B]
+  static constexpr int kOffBar = kOffStg + 4 * 2048;
+  static constexpr int kSmemBytes = kOffBar + 64 + 16;
+};
+
+template <int N>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
+dense_chain_kernel(const __grid_constant__ ChainParams P) {
+  using C = Cfg<N>;
+  using CC = ChainCfg<N>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + CC::kOffBar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + CC::kOffBar + 64);
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto bar_afull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto bar_wfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (uint32_t)(4 + s); };
+  const uint32_t bar_acc = bar0 + 8u * 6u;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_afull(s), 4);
+      mbar_init(bar_wfull(s), 1);
+      mbar_init(bar_empty(s), kCluster);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t crank = cluster_ctarank();
+
+  if (warp < 4) {
+    // =========================== operand producers and epilogue, layer by layer ===========================
+    const int lrow = lane >> 3, lq = lane & 7;
+    const long long row0 = (long long)blockIdx.x * kBM + warp * 32 + lrow;      // + 4 i
+    const int st_off = (lq >> 1) * kALbo + (warp * 32 + lrow) * 16 + (lq & 1) * 8;    // + 64 i
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint8_t* stg = smem + CC::kOffStg + warp * 2048;
+    const int orow = lane >> 2, och = lane & 3;
+    const long long row_base = (long long)blockIdx.x * kBM + warp * 32;
+    uint32_t sg = 0;                                         // slabs of the layers before this one
+    for (int l = 0; l < P.n_layers; ++l) {
+      const ChainLayer& Lr = P.layer[l];
+      const int n_slabs = (Lr.K1 + Lr.K2) / kSlabK;
+      auto load_slab = [&](int slab, float4 (&r)[2 * kKc]) {
+        const int k = slab * kSlabK;
+        const float* src = (k < Lr.K1) ? Lr.a1 + row0 * Lr.lda1 + k : Lr.a2 + row0 * Lr.lda2 + (k - Lr.K1);
+        const long long ld = (k < Lr.K1) ? Lr.lda1 : Lr.lda2;
+#pragma unroll
+        for (int i = 0; i < 2 * kKc; ++i)      // .cg: the previous layer's rows were written by this CTA a moment ago
+          r[i] = (row0 + 4 * i < P.M) ? __ldcg(reinterpret_cast<const float4*>(src + (long long)(4 * i) * ld) + lq)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto step = [&](int slab, const float4 (&r)[2 * kKc]) {
+        const uint32_t s = sg + (uint32_t)slab;
+        const int st = (int)(s % kStages);
+        mbar_wait(bar_empty(st), ((s / kStages) & 1u) ^ 1u, P.errflag, 41);
+        uint8_t* a_hi = smem + st * C::kStageBytes + st_off;
+        uint8_t* a_lo = a_hi + kAHalfBytes;
+#pragma unroll
+        for (int i = 0; i < 2 * kKc; ++i) {
+          uint2 hi, lo;
+          split4(r[i], hi, lo);
+          *reinterpret_cast<uint2*>(a_hi + i * 64) = hi;
+          *reinterpret_cast<uint2*>(a_lo + i * 64) = lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afull(st));
+      };
+      float4 r0[2 * kKc], r1[2 * kKc], r2[2 * kKc];
+      if (n_slabs > 0) load_slab(0, r0);
+      if (n_slabs > 1) load_slab(1, r1);
+      for (int slab = 0; slab < n_slabs; slab += 3) {
+        if (slab + 2 < n_slabs) load_slab(slab + 2, r2);
+        step(slab, r0);
+        if (slab + 1 >= n_slabs) break;
+        if (slab + 3 < n_slabs) load_slab(slab + 3, r0);
+        step(slab + 1, r1);
+        if (slab + 2 >= n_slabs) break;
+        if (slab + 4 < n_slabs) load_slab(slab + 4, r1);
+        step(slab + 2, r2);
+      }
+      sg += (uint32_t)n_slabs;
+      // ---- epilogue of layer l: TMEM lane = row; 32 x 64-byte blocks transposed through the warp's own shared memory
+      mbar_wait(bar_acc, (uint32_t)(l & 1), P.errflag, 42);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (Lr.bias) bj = __ldg(reinterpret_cast<const float4*>(Lr.bias + c0 + 4 * j));
+          float y[4] = {__uint_as_float(v[4 * j]) + bj.x, __uint_as_float(v[4 * j + 1]) + bj.y,
+                        __uint_as_float(v[4 * j + 2]) + bj.z, __uint_as_float(v[4 * j + 3]) + bj.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (P.act == 1) y[i] = fmaxf(y[i], 0.f);
+            else if (P.act == 2) y[i] = y[i] > 0.f ? y[i] : y[i] * P.slope;
+          }
+          *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = orow + 8 * k;
+          const float4 t = *reinterpret_cast<const float4*>(stg + r * 64 + ((och ^ ((r >> 1) & 3)) << 4));
+          if (row_base + r < P.M) *reinterpret_cast<float4*>(Lr.c + (row_base + r) * Lr.ldc + c0 + 4 * och) = t;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __threadfence_block();       // this warp's rows of layer l are the rows it loads for layer l + 1
+      __syncwarp();
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = make_idesc(0, kBM, N);
+    uint32_t sg = 0;
+    for (int l = 0; l < P.n_layers; ++l) {
+      const int n_slabs = (P.layer[l].K1 + P.layer[l].K2) / kSlabK;
+      for (int slab = 0; slab < n_slabs; ++slab) {
+        const uint32_t s = sg + (uint32_t)slab;
+        const int st = (int)(s % kStages);
+        const uint32_t par = (s / kStages) & 1u;
+        mbar_wait_backoff(bar_afull(st), par, P.errflag, 43, 32);
+        mbar_wait_backoff(bar_wfull(st), par, P.errflag, 44, 32);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + st * C::kStageBytes);
+          const uint64_t a_hi = make_smem_desc(sa, kALbo, 128);
+          const uint64_t a_lo = make_smem_desc(sa + kAHalfBytes, kALbo, 128);
+          const uint64_t b_hi = make_smem_desc(sa + 2 * kAHalfBytes, N * 16, 128);
+          const uint64_t b_lo = make_smem_desc(sa + 2 * kAHalfBytes + C::kWHalfBytes, N * 16, 128);
+#pragma unroll
+          for (int k = 0; k < kSlabK / 16; ++k) {
+            const uint64_t da = (uint64_t)((k * 2 * kALbo) >> 4);
+            const uint64_t db = (uint64_t)((k * 2 * N * 16) >> 4);
+            umma_f16(tmem_base, a_lo + da, b_hi + db, idesc, (slab | k) != 0 ? 1u : 0u);      // small terms first
+            umma_f16(tmem_base, a_hi + da, b_lo + db, idesc, 1u);
+            umma_f16(tmem_base, a_hi + da, b_hi + db, idesc, 1u);
+          }
+          umma_commit_mc(bar_empty(st), (uint16_t)((1u << kCluster) - 1u));
+          if (slab == n_slabs - 1) umma_commit(bar_acc);
+        }
+        __syncwarp();
+      }
+      sg += (uint32_t)n_slabs;
+    }
+  } else {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      uint32_t sg = 0;
+      for (int l = 0; l < P.n_layers; ++l) {
+        const int n_slabs = (P.layer[l].K1 + P.layer[l].K2) / kSlabK;
+        for (int slab = 0; slab < n_slabs; ++slab) {
+          const uint32_t s = sg + (uint32_t)slab;
+          const int st = (int)(s % kStages);
+          mbar_wait_backoff(bar_empty(st), ((s / kStages) & 1u) ^ 1u, P.errflag, 45);
+          mbar_expect_tx(bar_wfull(st), 2u * C::kWHalfBytes);
+          constexpr uint32_t part = 2u * C::kWHalfBytes / kCluster;
+          bulk_g2s_mc(smem_u32(smem + st * C::kStageBytes + 2 * kAHalfBytes) + crank * part,
+                      reinterpret_cast<const uint8_t*>(P.layer[l].w) + (size_t)slab * 2 * C::kWHalfBytes + (size_t)crank * part,
+                      part, bar_wfull(st), (uint16_t)((1u << kCluster) - 1u));
+        }
+        sg += (uint32_t)n_slabs;
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // no CTA may exit while a peer can still multicast into its shared memory
+  tc_fence_after();
+  if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
 template <int N>
 static int launch_n(const DenseParams& P, cudaStream_t st) {
   MRINR_SMEM_OPT_IN((dense_split_kernel<N>), Cfg<N>::kSmemBytes);
@@ -315,6 +533,34 @@ int run_pack_split(const float* w, int N, int K, uint16_t* out, cudaStream_t st)
   dense::pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, N, K, out);
   count_launch();
   return check_launch("pack_split");
+}
+
+// Chain of n layers with N = 256 outputs each in ONE launch: layer l reads a1[l] ([M,K1[l]], may be the output c[l-1] of
+// the previous layer) and the optional a2[l].  Returns MRINR_E_UNSUPPORTED for shapes the chain kernel does not take.
+int launch_dense_chain256(int n, const float* const* a1, const long long* lda1, const int* K1, const float* const* a2,
+                          const long long* lda2, const int* K2, const uint16_t* const* w_packed,
+                          const float* const* bias, float* const* c, const long long* ldc, int act, float slope,
+                          long long M, int32_t* errflag, cudaStream_t st) {
+  MRINR_REQUIRE(n >= 1 && n <= dense::kMaxChain, MRINR_E_UNSUPPORTED, "dense_chain: 1..%d layers (got %d)", dense::kMaxChain, n);
+  if (M <= 0) return 0;
+  dense::ChainParams P;
+  for (int l = 0; l < n; ++l) {
+    MRINR_REQUIRE(dense_split_supported(256, K1[l], K2[l]), MRINR_E_UNSUPPORTED, "dense_chain: unsupported K (%d + %d)", K1[l], K2[l]);
+    MRINR_REQUIRE(aligned16(a1[l]) && (K2[l] == 0 || aligned16(a2[l])) && aligned16(c[l]) && lda1[l] % 4 == 0 &&
+                      (K2[l] == 0 || lda2[l] % 4 == 0) && ldc[l] % 4 == 0 && (!bias[l] || aligned16(bias[l])),
+                  MRINR_E_ALIGN, "dense_chain: operands must be 16-byte aligned with row strides that are multiples of 4");
+    dense::ChainLayer& Lr = P.layer[l];
+    Lr.a1 = a1[l]; Lr.lda1 = lda1[l]; Lr.K1 = K1[l];
+    Lr.a2 = K2[l] ? a2[l] : nullptr; Lr.lda2 = K2[l] ? lda2[l] : 0; Lr.K2 = K2[l];
+    Lr.w = w_packed[l]; Lr.bias = bias[l]; Lr.c = c[l]; Lr.ldc = ldc[l];
+  }
+  P.n_layers = n; P.M = M; P.act = act; P.slope = slope; P.errflag = errflag;
+  MRINR_SMEM_OPT_IN((dense::dense_chain_kernel<256>), dense::ChainCfg<256>::kSmemBytes);
+  long long grid = (M + dense::kBM - 1) / dense::kBM;
+  grid = (grid + dense::kCluster - 1) / dense::kCluster * dense::kCluster;
+  dense::dense_chain_kernel<256><<<(unsigned)grid, dense::kThreads, dense::ChainCfg<256>::kSmemBytes, st>>>(P);
+  count_launch();
+  return check_launch("dense_chain");
 }
 
 // act: 0 none, 1 relu, 2 leaky relu (slope)
